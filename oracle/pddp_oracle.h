@@ -1,0 +1,100 @@
+/*
+ * pddp_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C, single-threaded CPU restatement of the reference's parallel-DDP/iLQR hot path
+ * (plancherb1/parallel-DDP @ 665d2d4), following the *GPU* control flow of
+ * DDPHelpers/DDPWrappers.cuh::runiLQR_GPU (best-alpha line search, real defect check,
+ * tree-ordered cost reduction).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg may load this library; the product (parallel-ddp_b200/) never does.
+ *
+ * Parity pin: oracle/liboracle.so (ORACLE_FMA=0) is checked bit-for-bit against the
+ * reference's own host instantiation of the same routines (oracle/_ref/ref_driver_N* `trace H`
+ * and `unit H`, fixtures in tests/golden/), and oracle/liboracle_fma.so (ORACLE_FMA=1, the
+ * fused-multiply-add pattern nvcc emits for the reference's device code) against the
+ * reference's GPU run (`trace G`, `unit G`) -- see tests/test_oracle_golden.py.
+ *
+ * All matrices are column-major with leading dimension = row count, per-knot arrays are
+ * contiguous [k][col][row] exactly as the reference allocates them (nisInitHelpers.cuh:776,797-798).
+ */
+#ifndef PDDP_ORACLE_H
+#define PDDP_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_ALPHA 64
+#define ORC_MAX_N 16   /* state size bound */
+#define ORC_MAX_M 8    /* control size bound */
+
+enum { ORC_PLANT_PEND = 1, ORC_PLANT_CART = 2, ORC_PLANT_QUAD = 3, ORC_PLANT_KUKA = 4 };
+enum { ORC_INT_EULER = 1, ORC_INT_MIDPOINT = 2, ORC_INT_RK3 = 3 };
+
+typedef struct {
+    int plant;            /* config.cuh:21-61 PLANT */
+    int n, m, npos;       /* STATE_SIZE, CONTROL_SIZE, NUM_POS */
+    int N;                /* NUM_TIME_STEPS (power of two, 32..1024: cudaUtils.h:187-207) */
+    int n_alpha;          /* NUM_ALPHA */
+    int M;                /* M_BLOCKS (= M_BLOCKS_B = M_BLOCKS_F, config.cuh:90-92) */
+    int integrator;       /* INTEGRATOR */
+    int max_iter;         /* MAX_ITER */
+    int expred_host_order;/* 1: sum dJexp like the reference's HOST build (bpHelpers.cuh:330-331), 0: like its kernel (:327-328,416) */
+    float dt;             /* (T)TIME_STEP */
+    float alpha[ORC_MAX_ALPHA]; /* (T)pow(ALPHA_BASE,i) nisInitHelpers.cuh:829 */
+    float rho_init, rho_min, rho_max, rho_factor;
+    float exp_red_min, exp_red_max, max_defect, tol_cost;
+    float Q1, Q2, R, QF1, QF2;   /* cost_arm.cuh:96-103 weights (other plants map theirs here) */
+    float I[252], Tbody[252];    /* Kuka spatial inertias / fixed joint transforms (dynamics_arm.cuh:71-427) */
+} orc_cfg;
+
+/* work arrays of one problem, reference layouts */
+typedef struct {
+    float *x, *u, *d;          /* [n_alpha][N][n|m|n] */
+    float *xp, *xp2, *up, *dp; /* [N][.] */
+    float *AB, *H, *g;         /* [N][n*(n+m)], [N][(n+m)^2], [N][n+m] */
+    float *P, *p, *Pp, *pp;    /* [N][n*n], [N][n] */
+    float *KT, *du, *ApBK, *Bdu;
+    float *xg;                 /* [n] */
+    float J[ORC_MAX_ALPHA], dT[ORC_MAX_ALPHA];
+    float dJexp[2*16];
+    int   err[16];
+    /* solver scalars */
+    float prevJ, dJ, z, rho, drho;
+    int   iter, alphaIndex, ignore_defect;
+} orc_ws;
+
+void  orc_default_cfg_kuka(orc_cfg *c, int N);                 /* headline constants, SURVEY A.1 (I/Tbody must be filled by caller) */
+orc_ws *orc_ws_alloc(const orc_cfg *c);
+void  orc_ws_free(orc_ws *w);
+
+/* plant plug-ins (Kuka) */
+void  orc_kuka_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd);                  /* dynamics_arm.cuh:2095-2163 */
+void  orc_kuka_dynamics_gradient(const orc_cfg *c, const float *x, const float *u, float *qdd, float *dqdd /*[147]*/); /* :2165-2289 */
+/* generic plant dispatch */
+void  orc_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd);
+void  orc_integrator(const orc_cfg *c, const float *x, const float *u, float *xnext);                 /* integrators.cuh */
+void  orc_integrator_gradient(const orc_cfg *c, const float *x, const float *u, float *AB, float *qdd_out);
+float orc_cost(const orc_cfg *c, const float *x, const float *u, const float *xg, int k);               /* cost_*.cuh costFunc */
+void  orc_cost_grad(const orc_cfg *c, float *H, float *g, const float *x, const float *u, const float *xg, int k);
+
+/* phases, operating on a workspace */
+void  orc_load(const orc_cfg *c, orc_ws *w, const float *x0, const float *u0, const float *xg);        /* loadVarsGPU, clear=1, rollout=0 */
+void  orc_init(const orc_cfg *c, orc_ws *w, float *Jout, int *alphaOut);                               /* initAlgGPU */
+int   orc_backward_pass(const orc_cfg *c, orc_ws *w);                                                   /* backwardPassGPU incl. rho retry */
+void  orc_backward_pass_once(const orc_cfg *c, orc_ws *w, float rho);                                   /* one backPassKern launch */
+void  orc_forward_sweep(const orc_cfg *c, orc_ws *w);                                                   /* forwardSweepKern, all alpha */
+void  orc_forward_sim(const orc_cfg *c, orc_ws *w);                                                     /* forwardSimKern, all (interval, alpha) */
+void  orc_cost_defect(const orc_cfg *c, orc_ws *w);                                                     /* costKern + defectKern */
+void  orc_line_search(const orc_cfg *c, orc_ws *w);                                                     /* fpHelpers.cuh:374-376,395-408 */
+int   orc_accept_reject(const orc_cfg *c, orc_ws *w, float *Jout, int *alphaOut);                       /* acceptRejectTrajGPU; returns 1 = stop */
+void  orc_next_iteration_setup(const orc_cfg *c, orc_ws *w);                                            /* nextIterationSetupGPU */
+
+/* whole solve: returns iterations used; x_out/u_out = accepted trajectory (storeVarsGPU) */
+int   orc_solve(const orc_cfg *c, const float *x0, const float *u0, const float *xg,
+                float *x_out, float *u_out, float *Jout /*[max_iter+1]*/, int *alphaOut /*[max_iter+1]*/);
+
+int   orc_fma_mode(void); /* the ORACLE_FMA this library was built with */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,77 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in tests/golden/ from the UNMODIFIED reference (oracle/_ref/ref_driver_N*,
+built by `make -C oracle ref` from /root/reference -- see oracle/Makefile).
+
+  python tests/golden/make_goldens.py host      # here (no GPU): reference HOST instantiation  -> *_H_*.npz
+  python tests/golden/make_goldens.py gpu       # on the GPU box (under gpurun): raw dumps       -> gpurun_out/golden_raw/*.bin
+  python tests/golden/make_goldens.py import    # here: gpurun_out/golden_raw/*.bin             -> *_G_*.npz
+
+Fixtures are compressed .npz files holding the named arrays ref_driver wrote; redundant broadcast copies
+(x1..x15 after `nis`/`init`) are dropped to keep them small."""
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refdump  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+RAW = os.path.join(ROOT, "gpurun_out", "golden_raw")
+_DROP = re.compile(r"it\d+\.(nis|init)\.[xud]([1-9]|1\d)$")
+
+
+def run(N, *args):
+    exe = os.path.join(REF, f"ref_driver_N{N}")
+    print("+", exe, *args, flush=True)
+    subprocess.run([exe, *[str(a) for a in args]], check=True, stdout=subprocess.DEVNULL)
+
+
+def to_npz(binpath, npzpath):
+    d = refdump.load(binpath)
+    d = {k: v for k, v in d.items() if not _DROP.search(k)}
+    np.savez_compressed(npzpath, **d)
+    print("  ->", os.path.relpath(npzpath, ROOT), f"{os.path.getsize(npzpath)/1024:.0f} KiB")
+
+
+def jobs(hw):
+    """(N, args-without-outfile, name)"""
+    t = "H" if hw == "H" else "G"
+    out = [(32, ("unit", t, 64, 7), f"unit_{t}"),
+           (32, ("trace", t, 0, 0.0, 2), f"trace_{t}_N32_s0_tol0"),
+           (32, ("trace", t, 3, 0.0001, 1), f"trace_{t}_N32_s3_tol1e-4"),
+           (128, ("trace", t, 0, 0.0, 1), f"trace_{t}_N128_s0_tol0")]
+    if hw == "G":
+        out += [(128, ("solve", "G", 0, 64, 0.0), "solve_G_N128_s0-63_tol0"),
+                (128, ("solve", "G", 0, 64, 0.0001), "solve_G_N128_s0-63_tol1e-4"),
+                (32, ("solve", "G", 0, 16, 0.0), "solve_G_N32_s0-15_tol0")]
+    return out
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == "host":
+        tmp = "/tmp/pddp_golden"; os.makedirs(tmp, exist_ok=True)
+        for N, args, name in jobs("H"):
+            b = os.path.join(tmp, name + ".bin")
+            run(N, *args, b)
+            to_npz(b, os.path.join(HERE, name + ".npz"))
+        d = refdump.load(os.path.join(tmp, "unit_H.bin"))
+        np.savez(os.path.join(HERE, "kuka_model.npz"), I=d["I"], Tbody=d["Tbody"])
+    elif mode == "gpu":
+        os.makedirs(RAW, exist_ok=True)
+        for N, args, name in jobs("G"):
+            run(N, *args, os.path.join(RAW, name + ".bin"))
+    elif mode == "import":
+        for f in sorted(os.listdir(RAW)):
+            if f.endswith(".bin"):
+                to_npz(os.path.join(RAW, f), os.path.join(HERE, f[:-4] + ".npz"))
+    else:
+        raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    main()
