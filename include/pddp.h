@@ -1,0 +1,111 @@
+/*
+ * pddp.h -- C-ABI of the B200-native batched parallel-DDP/iLQR solver (libpddp.so).
+ *
+ * Plain C, POD arguments only.  These entry points are what a binding of the reference's solver surface binds to;
+ * each one names the reference interface it replaces (paths relative to plancherb1/parallel-DDP @ 665d2d4).
+ * The reference has no ABI: its surface is a set of header-only C++ templates taking ~50 raw pointers
+ * (DDPHelpers/DDPWrappers.cuh:8-21).  include/pddp_shim.cuh re-creates those templates on top of this ABI so that
+ * examples/WAFR_iLQR_examples.cu compiles unchanged; INTEGRATION.md shows the ctypes / C++ bindings.
+ *
+ * Conventions: all matrices column-major, per-knot arrays contiguous [k][col][row] with leading dimension = row
+ * count (nisInitHelpers.cuh:776,797-798); a leading `batch` dimension is added in front of every per-problem array
+ * (the reference solves one problem per call).  Every function returns 0 on success or a negative PDDP_E_* code and
+ * never calls exit(); pddp_last_error() gives the message (the reference prints and exit()s, utils/cudaUtils.cu:31-37).
+ */
+#ifndef PDDP_H
+#define PDDP_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDDP_E_INVALID   (-1)   /* bad argument / unsupported configuration */
+#define PDDP_E_CUDA      (-2)   /* CUDA runtime error (message in pddp_last_error) */
+#define PDDP_E_NODEVICE  (-3)   /* no usable CUDA device: there is NO CPU fallback */
+
+#define PDDP_PLANT_PEND 1
+#define PDDP_PLANT_CART 2
+#define PDDP_PLANT_QUAD 3
+#define PDDP_PLANT_KUKA 4
+
+#define PDDP_MAX_ALPHA 32
+
+/* Run-time form of the reference's compile-time flag system (config.cuh:21-136). */
+typedef struct pddp_config {
+    int   plant;          /* PLANT (config.cuh:21-61); 4 = Kuka iiwa14 */
+    int   N;              /* NUM_TIME_STEPS: power of two in [32,1024] (cudaUtils.h:187-207 reduction trees) */
+    int   n_alpha;        /* NUM_ALPHA <= PDDP_MAX_ALPHA */
+    int   M;              /* M_BLOCKS = M_BLOCKS_B = M_BLOCKS_F (config.cuh:90-92), must divide N */
+    int   max_iter;       /* MAX_ITER (config.cuh:83) */
+    int   batch;          /* independent problems solved per call (new; the reference has none) */
+    int   device;         /* CUDA device ordinal */
+    int   integrator;     /* INTEGRATOR 1 Euler | 2 Midpoint | 3 RK3 (config.cuh:78-80) */
+    float alpha_base;     /* ALPHA_BASE: alpha_i = (float)pow(alpha_base, i) (nisInitHelpers.cuh:829) */
+    float total_time;     /* TOTAL_TIME: dt = (float)(total_time/(N-1)) (config.cuh:136) */
+    float rho_init, rho_min, rho_max, rho_factor;      /* config.cuh:98-104 */
+    float exp_red_min, exp_red_max;                    /* config.cuh:116-122 */
+    float max_defect;                                  /* MAX_DEFECT_SIZE (config.cuh:123-126) */
+    float tol_cost;                                    /* TOL_COST (config.cuh:85-87) */
+    float Q1, Q2, R, QF1, QF2;                         /* plants/cost_arm.cuh:96-103 */
+} pddp_config;
+
+typedef struct pddp_solver *pddp_handle;
+
+/* Fill *cfg with the reference's Kuka defaults for the WAFR iLQR example (config.cuh:43-58, WAFR_iLQR_examples.cu:4-11). */
+void pddp_default_config_kuka(pddp_config *cfg, int N, int batch);
+
+/* replaces allocateMemory_GPU (nisInitHelpers.cuh:766-861): owns every device array, stream and the model constants */
+int pddp_create(const pddp_config *cfg, pddp_handle *out);
+/* replaces freeMemory_GPU (nisInitHelpers.cuh:863-882) */
+void pddp_destroy(pddp_handle h);
+/* message of the last error on this handle (or of the last failed pddp_create when h == NULL) */
+const char *pddp_last_error(pddp_handle h);
+
+/* replaces runiLQR_GPU (DDPWrappers.cuh:8-138) for `batch` problems at once.
+ *   x0 [batch][N][n], u0 [batch][N][m], xGoal [batch][n]           HOST, reference layout (in)
+ *   x_out/u_out (may alias x0/u0: the reference overwrites x0,u0)   HOST (out)
+ *   Jout [batch][max_iter+1], alphaOut [batch][max_iter+1]         cost / chosen-alpha traces (-1 = rejected), unused
+ *                                                                   slots are left as NaN / -99
+ *   iters_out [batch]                                               iterations used per problem
+ *   times_ms[6]: total, sim, sweep, bp, nis, init  -- device time of each phase summed over iterations (CUDA events);
+ *                may be NULL.  rollout must be 0, clear must be 1 (warm starts are a "next" row). */
+int pddp_solve(pddp_handle h, const float *x0, const float *u0, const float *xGoal,
+               int forwardRolloutFlag, int clearVarsFlag, int ignoreFirstDefectFlag,
+               float *x_out, float *u_out, float *Jout, int *alphaOut, int *iters_out, double *times_ms);
+
+/* Same as pddp_solve but with inputs/outputs already resident on the device (used by bench.py's `value` leg). */
+int pddp_solve_device(pddp_handle h, const float *d_x0, const float *d_u0, const float *d_xGoal,
+                      int ignoreFirstDefectFlag, float *d_x_out, float *d_u_out, float *d_Jout, int *d_alphaOut,
+                      int *d_iters_out, double *times_ms);
+
+/* Synthetic inputs of the reference's benchmark driver (WAFR_iLQR_examples.cu:67-121) for problems seed0..seed0+batch-1,
+ * each drawn from std::default_random_engine(seed) exactly as the deterministic harness does. HOST buffers. */
+int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal);
+
+/* ---- plant plug-ins, evaluated on the device for n independent (x,u) samples (HOST buffers) -----------------------
+ * dynamics (plants/dynamics_arm.cuh:2095), _integratorGradient (utils/integrators.cuh:38-53) */
+int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int n, float *qdd);
+int pddp_unit_integrator_gradient(pddp_handle h, const float *x, const float *u, int n, float *AB, float *qdd);
+
+/* ---- phase-level entry points on the solver's device state (for knot-level parity tests and ncu captures) ----------
+ * The state is addressed by array name: "x","u","d" ([batch][n_alpha][N][.]), "xp","xp2","up","dp","AB","H","g","P","p",
+ * "Pp","pp","KT","du","ApBK","Bdu" ([batch][N][.]), "xGoal" ([batch][n]), "J","dT" ([batch][n_alpha]),
+ * "dJexp" ([batch][2M]) and the scalars "rho","drho","prevJ","dJ","z" (float [batch]), "iter","alphaIndex",
+ * "ignore_defect","done" (int [batch]).  All in the reference's layouts. */
+int pddp_set_array(pddp_handle h, const char *name, const void *host_src, long nbytes);
+int pddp_get_array(pddp_handle h, const char *name, void *host_dst, long nbytes);
+int pddp_phase_load_init(pddp_handle h, const float *x0, const float *u0, const float *xGoal, int ignoreFirstDefectFlag); /* loadVarsGPU + initAlgGPU */
+int pddp_phase_backward_pass(pddp_handle h);      /* backwardPassGPU      bpHelpers.cuh:484-517 */
+int pddp_phase_forward_sweep(pddp_handle h);      /* forwardSweepKern     fpHelpers.cuh:55-63   */
+int pddp_phase_forward_sim(pddp_handle h);        /* forwardSimKern + costKern + defectKern  fpHelpers.cuh:277-301,132-152,94-111 */
+int pddp_phase_line_search(pddp_handle h);        /* fpHelpers.cuh:374-376,395-408 + acceptRejectTrajGPU nisInitHelpers.cuh:487-518 */
+int pddp_phase_next_iteration(pddp_handle h);     /* nextIterationSetupGPU nisInitHelpers.cuh:245-279 */
+/* device time (ms) of the last phase call and the kernels it launched */
+int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
+
+/* number of kernels launched by the last pddp_solve* call on this handle */
+long pddp_last_launch_count(pddp_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

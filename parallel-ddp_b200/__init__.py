@@ -1,0 +1,219 @@
+"""parallel-ddp_b200 -- host-side mirror of the reference's solver surface over libpddp.so (C-ABI, include/pddp.h).
+
+The reference is header-only C++ (DDPHelpers/DDPWrappers.cuh); a Python binding does not exist upstream, so this module
+mirrors its entry points by name and argument meaning:
+
+    allocateMemory_GPU(...)  -> Solver(cfg)            nisInitHelpers.cuh:766
+    runiLQR_GPU(...)         -> Solver.runiLQR_GPU()   DDPWrappers.cuh:8
+    freeMemory_GPU(...)      -> Solver.freeMemory_GPU() nisInitHelpers.cuh:863
+
+There is NO CPU fallback: importing works anywhere (so the symbol table can be checked without a GPU), but creating a
+Solver without the compiled CUDA library or without a CUDA device raises PddpError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpddp.so")
+MAX_ALPHA = 32
+
+PLANT_PEND, PLANT_CART, PLANT_QUAD, PLANT_KUKA = 1, 2, 3, 4
+
+
+class PddpError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """pddp_config (include/pddp.h): run-time form of config.cuh."""
+    _fields_ = [("plant", C.c_int), ("N", C.c_int), ("n_alpha", C.c_int), ("M", C.c_int), ("max_iter", C.c_int),
+                ("batch", C.c_int), ("device", C.c_int), ("integrator", C.c_int),
+                ("alpha_base", C.c_float), ("total_time", C.c_float),
+                ("rho_init", C.c_float), ("rho_min", C.c_float), ("rho_max", C.c_float), ("rho_factor", C.c_float),
+                ("exp_red_min", C.c_float), ("exp_red_max", C.c_float), ("max_defect", C.c_float), ("tol_cost", C.c_float),
+                ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float)]
+
+
+EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
+           "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
+           "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count"]
+
+_lib = None
+FP = C.POINTER(C.c_float)
+IP = C.POINTER(C.c_int)
+DP = C.POINTER(C.c_double)
+
+
+def load_library():
+    """dlopen libpddp.so (built in-tree by parallel-ddp_b200/build.sh).  Raises PddpError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PddpError(f"{LIB_PATH} is missing: run parallel-ddp_b200/build.sh (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.pddp_default_config_kuka.argtypes = [C.POINTER(Config), C.c_int, C.c_int]; L.pddp_default_config_kuka.restype = None
+    L.pddp_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
+    L.pddp_destroy.argtypes = [H]; L.pddp_destroy.restype = None
+    L.pddp_last_error.argtypes = [H]; L.pddp_last_error.restype = C.c_char_p
+    L.pddp_solve.argtypes = [H, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, IP, IP, DP]
+    L.pddp_solve_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, DP]
+    L.pddp_make_inputs_kuka.argtypes = [C.c_int, C.c_int, C.c_uint, FP, FP, FP]
+    L.pddp_unit_dynamics.argtypes = [H, FP, FP, C.c_int, FP]
+    L.pddp_unit_integrator_gradient.argtypes = [H, FP, FP, C.c_int, FP, FP]
+    L.pddp_set_array.argtypes = [H, C.c_char_p, C.c_void_p, C.c_long]
+    L.pddp_get_array.argtypes = [H, C.c_char_p, C.c_void_p, C.c_long]
+    L.pddp_phase_load_init.argtypes = [H, FP, FP, FP, C.c_int]
+    for f in ("pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim", "pddp_phase_line_search", "pddp_phase_next_iteration"):
+        getattr(L, f).argtypes = [H]
+    L.pddp_last_phase_stats.argtypes = [H, DP, IP]
+    L.pddp_last_launch_count.argtypes = [H]; L.pddp_last_launch_count.restype = C.c_long
+    _lib = L
+    return L
+
+
+def default_config_kuka(N=128, batch=1, **over):
+    L = load_library()
+    c = Config()
+    L.pddp_default_config_kuka(C.byref(c), N, batch)
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def _f(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(FP)
+
+
+def make_inputs_kuka(N, batch, seed0=0):
+    """Synthetic benchmark inputs (WAFR_iLQR_examples.cu:67-121), one std::default_random_engine(seed) per problem."""
+    L = load_library()
+    x0 = np.zeros((batch, N, 14), np.float32); u0 = np.zeros((batch, N, 7), np.float32); xg = np.zeros((batch, 14), np.float32)
+    L.pddp_make_inputs_kuka(N, batch, seed0, x0.ctypes.data_as(FP), u0.ctypes.data_as(FP), xg.ctypes.data_as(FP))
+    return x0, u0, xg
+
+
+class Solver:
+    """Owns every device array of `batch` problems (what allocateMemory_GPU hands back as ~50 raw pointers)."""
+    _SHAPES = None
+
+    def __init__(self, cfg):
+        self.L = load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.L.pddp_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise PddpError(f"pddp_create failed ({rc}): {self.L.pddp_last_error(None).decode()}")
+        B, N, A, M = cfg.batch, cfg.N, cfg.n_alpha, cfg.M
+        n, m = 14, 7
+        nm = n + m
+        self.n, self.m = n, m
+        f, i = np.float32, np.int32
+        self.shapes = dict(x=((B, A, N, n), f), u=((B, A, N, m), f), d=((B, A, N, n), f), xp=((B, N, n), f), xp2=((B, N, n), f),
+                           up=((B, N, m), f), dp=((B, N, n), f), AB=((B, N, nm, n), f), H=((B, N, nm, nm), f), g=((B, N, nm), f),
+                           P=((B, N, n, n), f), p=((B, N, n), f), Pp=((B, N, n, n), f), pp=((B, N, n), f), KT=((B, N, m, n), f),
+                           du=((B, N, m), f), ApBK=((B, N, n, n), f), Bdu=((B, N, n), f), xGoal=((B, n), f), costk=((B, A, N), f),
+                           J=((B, A), f), dT=((B, A), f), dJexp=((B, 2 * M), f), rho=((B,), f), drho=((B,), f), prevJ=((B,), f),
+                           dJ=((B,), f), z=((B,), f), iter=((B,), i), alphaIndex=((B,), i), ignore_defect=((B,), i), done=((B,), i),
+                           accepted=((B,), i), final_src=((B,), i), Jout=((B, cfg.max_iter + 1), f), alphaOut=((B, cfg.max_iter + 1), i))
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise PddpError(f"{what} failed ({rc}): {self.L.pddp_last_error(self.h).decode()}")
+
+    # ---- solver entry point -------------------------------------------------------------------------------------
+    def runiLQR_GPU(self, x0, u0, xGoal, forwardRolloutFlag=0, clearVarsFlag=1, ignoreFirstDefectFlag=1, want_times=False):
+        """Batched runiLQR_GPU.  x0 [B,N,14], u0 [B,N,7], xGoal [B,14] (or [14]).  Returns dict(x, u, Jout, alphaOut, iters[, times_ms])."""
+        B, N = self.cfg.batch, self.cfg.N
+        x0, px = _f(np.broadcast_to(x0, (B, N, 14))); u0, pu = _f(np.broadcast_to(u0, (B, N, 7))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        L1 = self.cfg.max_iter + 1
+        x = np.empty((B, N, 14), np.float32); u = np.empty((B, N, 7), np.float32)
+        Jout = np.empty((B, L1), np.float32); aOut = np.empty((B, L1), np.int32); iters = np.empty(B, np.int32)
+        times = np.zeros(6, np.float64)
+        rc = self.L.pddp_solve(self.h, px, pu, pg, forwardRolloutFlag, clearVarsFlag, ignoreFirstDefectFlag,
+                               x.ctypes.data_as(FP), u.ctypes.data_as(FP), Jout.ctypes.data_as(FP), aOut.ctypes.data_as(IP),
+                               iters.ctypes.data_as(IP), times.ctypes.data_as(DP) if want_times else None)
+        self._ck(rc, "pddp_solve")
+        out = dict(x=x, u=u, Jout=Jout, alphaOut=aOut, iters=iters)
+        if want_times:
+            out["times_ms"] = dict(zip(("total", "sim", "sweep", "bp", "nis", "init"), times))
+        return out
+
+    def solve_device(self, d_x0, d_u0, d_xg, d_x, d_u, d_J, d_a, d_it, ignoreFirstDefectFlag=1, times=None):
+        """Device-resident variant: arguments are raw device pointers (ints)."""
+        rc = self.L.pddp_solve_device(self.h, d_x0, d_u0, d_xg, ignoreFirstDefectFlag, d_x, d_u, d_J, d_a, d_it,
+                                      times.ctypes.data_as(DP) if times is not None else None)
+        self._ck(rc, "pddp_solve_device")
+
+    def launch_count(self):
+        return int(self.L.pddp_last_launch_count(self.h))
+
+    # ---- plant plug-ins -----------------------------------------------------------------------------------------
+    def dynamics(self, x, u):
+        x, px = _f(x); u, pu = _f(u); n = x.shape[0]
+        qdd = np.empty((n, 7), np.float32)
+        self._ck(self.L.pddp_unit_dynamics(self.h, px, pu, n, qdd.ctypes.data_as(FP)), "pddp_unit_dynamics")
+        return qdd
+
+    def integratorGradient(self, x, u):
+        x, px = _f(x); u, pu = _f(u); n = x.shape[0]
+        AB = np.empty((n, 21, 14), np.float32); qdd = np.empty((n, 7), np.float32)
+        self._ck(self.L.pddp_unit_integrator_gradient(self.h, px, pu, n, AB.ctypes.data_as(FP), qdd.ctypes.data_as(FP)), "pddp_unit_integrator_gradient")
+        return AB, qdd
+
+    # ---- phase-level access -------------------------------------------------------------------------------------
+    def get(self, name):
+        shp, dt = self.shapes[name]
+        a = np.empty(shp, dt)
+        self._ck(self.L.pddp_get_array(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes), f"get {name}")
+        return a
+
+    def set(self, name, value):
+        shp, dt = self.shapes[name]
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shp))
+        self._ck(self.L.pddp_set_array(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), a.nbytes), f"set {name}")
+
+    def load_init(self, x0, u0, xGoal, ignoreFirstDefectFlag=1):
+        B, N = self.cfg.batch, self.cfg.N
+        x0, px = _f(np.broadcast_to(x0, (B, N, 14))); u0, pu = _f(np.broadcast_to(u0, (B, N, 7))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        self._ck(self.L.pddp_phase_load_init(self.h, px, pu, pg, ignoreFirstDefectFlag), "load_init")
+
+    def backwardPassGPU(self):
+        self._ck(self.L.pddp_phase_backward_pass(self.h), "backward_pass")
+
+    def forwardSweep(self):
+        self._ck(self.L.pddp_phase_forward_sweep(self.h), "forward_sweep")
+
+    def forwardSimGPU(self):
+        self._ck(self.L.pddp_phase_forward_sim(self.h), "forward_sim")
+        self._ck(self.L.pddp_phase_line_search(self.h), "line_search")
+
+    def forwardSimOnly(self):
+        self._ck(self.L.pddp_phase_forward_sim(self.h), "forward_sim")
+
+    def lineSearchAcceptReject(self):
+        self._ck(self.L.pddp_phase_line_search(self.h), "line_search")
+
+    def nextIterationSetupGPU(self):
+        self._ck(self.L.pddp_phase_next_iteration(self.h), "next_iteration")
+
+    def last_phase_ms(self):
+        ms = C.c_double(); n = C.c_int()
+        self.L.pddp_last_phase_stats(self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def freeMemory_GPU(self):
+        if self.h:
+            self.L.pddp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.freeMemory_GPU()
+        except Exception:
+            pass

@@ -1,0 +1,398 @@
+// pddp_api.cu -- host side of libpddp.so: the C-ABI declared in include/pddp.h over the kernels in kernels.cuh.
+// The host code is C++ (the reference is compiled C++/CUDA); there is no CPU fallback: every entry point fails
+// with PDDP_E_NODEVICE / PDDP_E_CUDA when no device can run the kernels.
+#include "../../include/pddp.h"
+#include "kernels.cuh"
+#include "kuka_model_data.inc"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+using namespace pddp;
+
+static thread_local std::string g_create_error;
+
+struct pddp_solver {
+    pddp_config cfg;
+    DevState S;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    std::string err;
+    int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
+    long launches = 0;
+    int n, m;
+    float *d_xout = nullptr, *d_uout = nullptr; int *d_iters = nullptr;
+    float *h_stage = nullptr; size_t h_stage_bytes = 0;    // pinned staging
+    int *h_nactive = nullptr;
+    cudaEvent_t ev[8];
+    double last_ms = 0; int last_launches = 0;
+    size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
+    std::map<std::string, std::pair<void*, size_t>> arrays;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess){ h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return PDDP_E_CUDA; } } while (0)
+
+extern "C" void pddp_default_config_kuka(pddp_config *c, int N, int batch){
+    std::memset(c, 0, sizeof(*c));
+    c->plant = PDDP_PLANT_KUKA; c->N = N; c->n_alpha = 16; c->M = 4; c->max_iter = 100; c->batch = batch; c->device = 0;
+    c->integrator = 1; c->alpha_base = 0.5f; c->total_time = 0.5f;
+    c->rho_init = (float)12.5; c->rho_min = (float)0.01; c->rho_max = (float)10000000.0; c->rho_factor = (float)1.25;
+    c->exp_red_min = (float)0.05; c->exp_red_max = (float)1.25; c->max_defect = (float)1.0; c->tol_cost = 0.0f;
+    c->Q1 = (float)0.1; c->Q2 = (float)0.001; c->R = (float)0.0001; c->QF1 = (float)1000.0; c->QF2 = (float)1000.0;
+}
+
+extern "C" const char *pddp_last_error(pddp_handle h){ return h ? h->err.c_str() : g_create_error.c_str(); }
+
+template <typename T>
+static int dalloc(pddp_handle h, T **p, size_t count, const char *name = nullptr, bool zero = true){
+    CK(cudaMalloc((void**)p, count*sizeof(T)));
+    h->allocs.push_back(*p);
+    if (zero){ CK(cudaMemset(*p, 0, count*sizeof(T))); }
+    if (name){ h->arrays[name] = {(void*)*p, count*sizeof(T)}; }
+    return 0;
+}
+
+extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
+    *out = nullptr;
+    auto fail = [&](const std::string &msg, int code){ g_create_error = msg; return code; };
+    if (!cfg){ return fail("null config", PDDP_E_INVALID); }
+    if (cfg->plant != PDDP_PLANT_KUKA){ return fail("only PLANT 4 (Kuka iiwa14) has device kernels in this build", PDDP_E_INVALID); }
+    if (cfg->integrator != 1){ return fail("only the Euler integrator (INTEGRATOR 1, the Kuka default) is built", PDDP_E_INVALID); }
+    if (cfg->N < 32 || cfg->N > 1024 || (cfg->N & (cfg->N-1))){ return fail("N must be a power of two in [32,1024]", PDDP_E_INVALID); }
+    if (cfg->M < 1 || cfg->M > 8 || cfg->N % cfg->M){ return fail("M must divide N and be <= 8", PDDP_E_INVALID); }
+    if (cfg->n_alpha < 1 || cfg->n_alpha > PDDP_MAX_ALPHA){ return fail("n_alpha out of range", PDDP_E_INVALID); }
+    if (cfg->batch < 1 || cfg->max_iter < 1){ return fail("batch and max_iter must be positive", PDDP_E_INVALID); }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0){ cudaGetLastError(); return fail("no CUDA device (this library has no CPU path)", PDDP_E_NODEVICE); }
+    if (cfg->device < 0 || cfg->device >= ndev){ return fail("bad device ordinal", PDDP_E_INVALID); }
+    pddp_handle h = new pddp_solver();
+    h->cfg = *cfg; h->n = kuka::NX; h->m = kuka::NU;
+    auto bail = [&](int code){ g_create_error = h->err; for (void *p : h->allocs){ cudaFree(p); } delete h; return code; };
+    #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess){ h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(PDDP_E_CUDA); } } while (0)
+    CKC(cudaSetDevice(cfg->device));
+    CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev){ CKC(cudaEventCreate(&e)); }
+    DevState &S = h->S; std::memset(&S, 0, sizeof(S));
+    const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m, nm = n + m;
+    S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter;
+    S.dt = (float)((double)cfg->total_time/(double)(N-1));          // (T)TIME_STEP, config.cuh:136
+    S.tol_cost = cfg->tol_cost; S.two_tol = (float)(2*(double)cfg->tol_cost);
+    S.rho_min = cfg->rho_min; S.rho_max = cfg->rho_max; S.rho_factor = cfg->rho_factor; S.inv_rho_factor = (float)(1.0/(double)cfg->rho_factor);
+    S.exp_red_min = cfg->exp_red_min; S.exp_red_max = cfg->exp_red_max; S.max_defect = cfg->max_defect;
+    S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2;
+    float *dI, *dTb, *dal;
+    #define DA(ptr, count, name) do { if (dalloc(h, &(ptr), (size_t)(count), name)){ return bail(PDDP_E_CUDA); } } while (0)
+    DA(dI, 252, nullptr); DA(dTb, 252, nullptr); DA(dal, PDDP_MAX_ALPHA, nullptr);
+    std::vector<float> al(PDDP_MAX_ALPHA, 0.f);
+    for (int i = 0; i < A; i++){ al[i] = (float)std::pow((double)cfg->alpha_base, i); }    // nisInitHelpers.cuh:829
+    CKC(cudaMemcpy(dI, KUKA_I_DATA, sizeof(KUKA_I_DATA), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(dTb, KUKA_TBODY_DATA, sizeof(KUKA_TBODY_DATA), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(dal, al.data(), al.size()*sizeof(float), cudaMemcpyHostToDevice));
+    S.I = dI; S.Tbody = dTb; S.alpha = dal;
+    DA(S.x, (size_t)B*A*N*n, "x"); DA(S.u, (size_t)B*A*N*m, "u"); DA(S.d, (size_t)B*A*N*n, "d");
+    DA(S.xp, (size_t)B*N*n, "xp"); DA(S.xp2, (size_t)B*N*n, "xp2"); DA(S.up, (size_t)B*N*m, "up"); DA(S.dp, (size_t)B*N*n, "dp");
+    DA(S.AB, (size_t)B*N*n*nm, "AB"); DA(S.H, (size_t)B*N*nm*nm, "H"); DA(S.g, (size_t)B*N*nm, "g");
+    DA(S.Pbuf[0], (size_t)B*N*n*n, nullptr); DA(S.Pbuf[1], (size_t)B*N*n*n, nullptr); DA(S.pbuf[0], (size_t)B*N*n, nullptr); DA(S.pbuf[1], (size_t)B*N*n, nullptr);
+    DA(S.KT, (size_t)B*N*n*m, "KT"); DA(S.du, (size_t)B*N*m, "du"); DA(S.ApBK, (size_t)B*N*n*n, "ApBK"); DA(S.Bdu, (size_t)B*N*n, "Bdu");
+    DA(S.xGoal, (size_t)B*n, "xGoal"); DA(S.costk, (size_t)B*A*N, "costk");
+    DA(S.J, (size_t)B*A, "J"); DA(S.dT, (size_t)B*A, "dT"); DA(S.dJexp, (size_t)B*2*M, "dJexp");
+    DA(S.rho, B, "rho"); DA(S.drho, B, "drho"); DA(S.prevJ, B, "prevJ"); DA(S.dJ, B, "dJ"); DA(S.z, B, "z");
+    DA(S.iter, B, "iter"); DA(S.alphaIndex, B, "alphaIndex"); DA(S.ignore_defect, B, "ignore_defect"); DA(S.done, B, "done");
+    DA(S.accepted, B, "accepted"); DA(S.final_src, B, "final_src");
+    DA(S.Jout, (size_t)B*(cfg->max_iter+1), "Jout"); DA(S.alphaOut, (size_t)B*(cfg->max_iter+1), "alphaOut");
+    DA(S.n_active, 1, nullptr);
+    DA(h->d_xout, (size_t)B*N*n, nullptr); DA(h->d_uout, (size_t)B*N*m, nullptr); DA(h->d_iters, B, nullptr);
+    h->h_stage_bytes = ((size_t)B*N*(n+m) + (size_t)B*n + (size_t)2*B*(cfg->max_iter+1) + B)*sizeof(float);
+    CKC(cudaMallocHost((void**)&h->h_stage, h->h_stage_bytes));
+    CKC(cudaMallocHost((void**)&h->h_nactive, sizeof(int)));
+    // dynamic shared memory of each kernel
+    h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
+    h->smem_sweep = ((size_t)(N-1)*n*n + (size_t)(N-1)*n + (size_t)2*N*n)*sizeof(float);
+    h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*sizeof(SimWarpSmem);
+    h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
+    h->smem_nis = 2*36*kuka::NB*sizeof(float) + NIS_WARPS*sizeof(NisWarpSmem);
+    h->smem_udyn = 2*36*kuka::NB*sizeof(float) + sizeof(SimWarpSmem);
+    h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + sizeof(NisWarpSmem);
+    if (h->smem_sweep > 227*1024){ h->err = "N too large for the single-pass sweep staging"; return bail(PDDP_E_INVALID); }
+    CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
+    CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
+    CKC(cudaFuncSetAttribute(sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sel));
+    CKC(cudaFuncSetAttribute(nis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nis));
+    CKC(cudaFuncSetAttribute(unit_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_udyn));
+    CKC(cudaFuncSetAttribute(unit_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ugrad));
+    CKC(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+extern "C" void pddp_destroy(pddp_handle h){
+    if (!h){ return; }
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs){ cudaFree(p); }
+    if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
+    for (auto &e : h->ev){ cudaEventDestroy(e); }
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ---------------------------------------------------------------------------------------------------- launches
+__global__ void reset_kernel(DevState S, float rho_init, int ignore_first){
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i <= S.max_iter; i += blockDim.x){ S.Jout[(size_t)b*(S.max_iter+1)+i] = nanf(""); S.alphaOut[(size_t)b*(S.max_iter+1)+i] = -99; }
+    if (threadIdx.x == 0){
+        S.rho[b] = rho_init; S.drho[b] = 1.0f; S.iter[b] = 1; S.alphaIndex[b] = 0; S.ignore_defect[b] = ignore_first; S.done[b] = 0;
+        S.accepted[b] = 0; S.final_src[b] = -1; S.dJ[b] = 0.f; S.z[b] = 0.f; S.prevJ[b] = 0.f;
+        if (b == 0){ *S.n_active = S.B; }
+    }
+}
+
+static int launch_reset(pddp_handle h, int ignore_first){
+    DevState &S = h->S; const int B = S.B, N = S.N, A = S.A, n = S.n, m = S.m;
+    // loadVarsGPU with clearVarsFlag=1 (nisInitHelpers.cuh:612-634)
+    CK(cudaMemsetAsync(S.Pbuf[0], 0, (size_t)B*N*n*n*4, h->stream)); CK(cudaMemsetAsync(S.Pbuf[1], 0, (size_t)B*N*n*n*4, h->stream));
+    CK(cudaMemsetAsync(S.pbuf[0], 0, (size_t)B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.pbuf[1], 0, (size_t)B*N*n*4, h->stream));
+    CK(cudaMemsetAsync(S.KT, 0, (size_t)B*N*n*m*4, h->stream)); CK(cudaMemsetAsync(S.du, 0, (size_t)B*N*m*4, h->stream));
+    CK(cudaMemsetAsync(S.d, 0, (size_t)B*A*N*n*4, h->stream)); CK(cudaMemsetAsync(S.dp, 0, (size_t)B*N*n*4, h->stream));
+    CK(cudaMemsetAsync(S.dT, 0, (size_t)B*A*4, h->stream));
+    reset_kernel<<<B, 128, 0, h->stream>>>(S, h->cfg.rho_init, ignore_first);
+    h->cur = 0; h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_init(pddp_handle h){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
+    DevState &S = h->S;
+    nis_kernel<<<(S.B*S.N + NIS_WARPS - 1)/NIS_WARPS, 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1);
+    init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S);
+    select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_bp(pddp_handle h){
+    DevState &S = h->S; h->cur ^= 1;
+    bp_kernel<kuka::NX, kuka::NU><<<S.B*S.M, BP_THREADS, h->smem_bp, h->stream>>>(S, h->cur);
+    h->launches += 1; CK(cudaGetLastError()); return 0;
+}
+static int launch_sweep(pddp_handle h){
+    DevState &S = h->S; if (S.M == 1){ return 0; }
+    sweep_kernel<kuka::NX><<<S.B, 32*S.A, h->smem_sweep, h->stream>>>(S);
+    h->launches += 1; CK(cudaGetLastError()); return 0;
+}
+static int launch_sim(pddp_handle h){
+    DevState &S = h->S;
+    sim_kernel<<<S.B*S.A, 32*S.M, h->smem_sim, h->stream>>>(S);
+    h->launches += 1; CK(cudaGetLastError()); return 0;
+}
+static int launch_select(pddp_handle h){
+    DevState &S = h->S;
+    select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 0);
+    h->launches += 1; CK(cudaGetLastError()); return 0;
+}
+static int launch_nis(pddp_handle h){
+    DevState &S = h->S;
+    nis_kernel<<<(S.B*S.N + NIS_WARPS - 1)/NIS_WARPS, 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 0, 0);
+    h->launches += 1; CK(cudaGetLastError()); return 0;
+}
+
+// the iteration loop of runiLQR_GPU (DDPWrappers.cuh:52-114) with all host decisions moved to select_kernel
+static int run_iterations(pddp_handle h, double *times_ms){
+    DevState &S = h->S;
+    const bool timing = times_ms != nullptr;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&](){ if (timing){ cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); } };
+    const bool poll = h->cfg.tol_cost > 0.0f;
+    int it_done = 0;
+    for (int it = 0; it < S.max_iter; it++){
+        int rc;
+        mark(); if ((rc = launch_bp(h))){ return rc; }
+        mark(); if ((rc = launch_sweep(h))){ return rc; }
+        mark(); if ((rc = launch_sim(h))){ return rc; }
+        mark(); if ((rc = launch_select(h))){ return rc; }
+        mark(); if ((rc = launch_nis(h))){ return rc; }
+        it_done = it + 1;
+        if (poll && (it % 4) == 3){
+            // convergence-driven early exit: look at the active-problem counter without draining the pipeline more than needed
+            CK(cudaMemcpyAsync(h->h_nactive, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            if (*h->h_nactive == 0){ break; }
+        }
+    }
+    mark();
+    if (timing){
+        CK(cudaStreamSynchronize(h->stream));
+        double acc[5] = {0,0,0,0,0};
+        for (int it = 0; it < it_done; it++){ for (int ph = 0; ph < 5; ph++){ float ms = 0; cudaEventElapsedTime(&ms, evs[it*5+ph], evs[it*5+ph+1]); acc[ph] += ms; } }
+        for (auto e : evs){ cudaEventDestroy(e); }
+        // reference order of the timing outputs: tTime, simTime, sweepTime, bpTime, nisTime, initTime (DDPWrappers.cuh:11)
+        times_ms[1] = acc[2] + acc[3]; times_ms[2] = acc[1]; times_ms[3] = acc[0]; times_ms[4] = acc[4];
+    }
+    return 0;
+}
+
+extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *d_u0, const float *d_xGoal, int ignoreFirstDefectFlag,
+                                 float *d_x_out, float *d_u_out, float *d_Jout, int *d_alphaOut, int *d_iters_out, double *times_ms){
+    if (!h){ return PDDP_E_INVALID; }
+    DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m; int rc;
+    CK(cudaSetDevice(h->cfg.device));
+    h->launches = 0;
+    CK(cudaEventRecord(h->ev[0], h->stream));
+    if ((rc = launch_reset(h, ignoreFirstDefectFlag))){ return rc; }
+    CK(cudaMemcpyAsync(S.xp, d_x0, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.up, d_u0, (size_t)B*N*m*4, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.xGoal, d_xGoal, (size_t)B*n*4, cudaMemcpyDeviceToDevice, h->stream));
+    if ((rc = launch_init(h))){ return rc; }
+    CK(cudaEventRecord(h->ev[1], h->stream));
+    if ((rc = run_iterations(h, times_ms))){ return rc; }
+    CK(cudaEventRecord(h->ev[2], h->stream));
+    store_kernel<<<B, 256, 0, h->stream>>>(S, d_x_out ? d_x_out : h->d_xout, d_u_out ? d_u_out : h->d_uout, d_iters_out ? d_iters_out : h->d_iters);
+    h->launches += 1; CK(cudaGetLastError());
+    if (d_Jout){ CK(cudaMemcpyAsync(d_Jout, S.Jout, (size_t)B*(S.max_iter+1)*4, cudaMemcpyDeviceToDevice, h->stream)); }
+    if (d_alphaOut){ CK(cudaMemcpyAsync(d_alphaOut, S.alphaOut, (size_t)B*(S.max_iter+1)*4, cudaMemcpyDeviceToDevice, h->stream)); }
+    CK(cudaEventRecord(h->ev[3], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (times_ms){
+        float t_all = 0, t_init = 0, t_store = 0;
+        cudaEventElapsedTime(&t_all, h->ev[0], h->ev[3]); cudaEventElapsedTime(&t_init, h->ev[0], h->ev[1]); cudaEventElapsedTime(&t_store, h->ev[2], h->ev[3]);
+        times_ms[0] = t_all; times_ms[5] = t_init + t_store;
+    }
+    return 0;
+}
+
+extern "C" int pddp_solve(pddp_handle h, const float *x0, const float *u0, const float *xGoal, int forwardRolloutFlag, int clearVarsFlag,
+                          int ignoreFirstDefectFlag, float *x_out, float *u_out, float *Jout, int *alphaOut, int *iters_out, double *times_ms){
+    if (!h){ return PDDP_E_INVALID; }
+    if (forwardRolloutFlag != 0 || clearVarsFlag != 1){ h->err = "rollout / warm-start modes are not built yet (forwardRolloutFlag=0, clearVarsFlag=1 only)"; return PDDP_E_INVALID; }
+    if (!x0 || !u0 || !xGoal){ h->err = "null input"; return PDDP_E_INVALID; }
+    DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m, L = S.max_iter + 1; int rc;
+    CK(cudaSetDevice(h->cfg.device));
+    // host -> pinned staging -> device (inputs), device -> pinned -> host (results): all inside the caller-visible time
+    float *st = h->h_stage; float *sx = st, *su = sx + (size_t)B*N*n, *sg = su + (size_t)B*N*m;
+    float *sJ = sg + (size_t)B*n; int *sA = reinterpret_cast<int*>(sJ + (size_t)B*L); int *sI = sA + (size_t)B*L;
+    std::memcpy(sx, x0, (size_t)B*N*n*4); std::memcpy(su, u0, (size_t)B*N*m*4); std::memcpy(sg, xGoal, (size_t)B*n*4);
+    // inputs travel to scratch device buffers (d_xout/d_uout double as input staging), then the device path runs
+    CK(cudaMemcpyAsync(h->d_xout, sx, (size_t)B*N*n*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_uout, su, (size_t)B*N*m*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.xGoal, sg, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = pddp_solve_device(h, h->d_xout, h->d_uout, S.xGoal, ignoreFirstDefectFlag, nullptr, nullptr, nullptr, nullptr, nullptr, times_ms))){ return rc; }
+    CK(cudaMemcpyAsync(sx, h->d_xout, (size_t)B*N*n*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(su, h->d_uout, (size_t)B*N*m*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sJ, S.Jout, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sA, S.alphaOut, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(sI, h->d_iters, (size_t)B*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (x_out){ std::memcpy(x_out, sx, (size_t)B*N*n*4); } if (u_out){ std::memcpy(u_out, su, (size_t)B*N*m*4); }
+    if (Jout){ std::memcpy(Jout, sJ, (size_t)B*L*4); } if (alphaOut){ std::memcpy(alphaOut, sA, (size_t)B*L*4); }
+    if (iters_out){ std::memcpy(iters_out, sI, (size_t)B*4); }
+    return 0;
+}
+
+extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
+
+// WAFR_iLQR_examples.cu:67-121 with one std::default_random_engine(seed) per problem (the deterministic harness' inputs)
+extern "C" int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal){
+    const double PI = 3.14159;
+    const float q0[7] = {(float)(-0.5*PI), (float)(0.25*PI), (float)(0.167*PI), (float)(-0.167*PI), (float)(0.125*PI), (float)(0.167*PI), (float)(0.5*PI)};
+    const float uu[7] = {(float)0.0, (float)-102.9832, (float)11.1968, (float)47.0724, (float)2.5993, (float)-7.0290, (float)-0.0907};
+    const float xg[14] = {0, 0, 0, (float)(-0.25*PI), 0, (float)(0.25*PI), (float)(0.5*PI), 0, 0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < batch; b++){
+        std::default_random_engine eng(seed0 + b);
+        std::normal_distribution<double> dist(0.0, 0.001);
+        for (int k = 0; k < N; k++){
+            float *xk = x0 + ((size_t)b*N + k)*14;
+            for (int i = 0; i < 7; i++){ xk[i] = q0[i]; }
+            for (int i = 0; i < 7; i++){ xk[7+i] = static_cast<float>(dist(eng)); }
+            float *uk = u0 + ((size_t)b*N + k)*7;
+            for (int i = 0; i < 7; i++){ uk[i] = uu[i]; }
+        }
+        for (int i = 0; i < 14; i++){ xGoal[(size_t)b*14 + i] = xg[i]; }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- plug-in unit calls
+extern "C" int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int nsamp, float *qdd){
+    if (!h || nsamp < 1){ return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    float *dx, *du, *dq;
+    CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4));
+    CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
+    unit_dynamics_kernel<<<nsamp < 1184 ? nsamp : 1184, 32, h->smem_udyn, h->stream>>>(h->S.I, h->S.Tbody, dx, du, nsamp, dq);
+    CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(du); cudaFree(dq);
+    return 0;
+}
+extern "C" int pddp_unit_integrator_gradient(pddp_handle h, const float *x, const float *u, int nsamp, float *AB, float *qdd){
+    if (!h || nsamp < 1){ return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    float *dx, *du, *dq, *dab;
+    CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4)); CK(cudaMalloc(&dab, (size_t)nsamp*294*4));
+    CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
+    unit_gradient_kernel<<<nsamp < 888 ? nsamp : 888, 32, h->smem_ugrad, h->stream>>>(h->S.I, h->S.Tbody, dx, du, nsamp, h->S.dt, dab, dq);
+    CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(AB, dab, (size_t)nsamp*294*4, cudaMemcpyDeviceToHost));
+    if (qdd){ CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost)); }
+    cudaFree(dx); cudaFree(du); cudaFree(dq); cudaFree(dab);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- phase-level access
+static bool resolve(pddp_handle h, const char *name, void **p, size_t *bytes){
+    std::string s(name); DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n;
+    if (s == "P"){ *p = S.Pbuf[h->cur]; *bytes = B*N*n*n*4; return true; }
+    if (s == "Pp"){ *p = S.Pbuf[h->cur^1]; *bytes = B*N*n*n*4; return true; }
+    if (s == "p"){ *p = S.pbuf[h->cur]; *bytes = B*N*n*4; return true; }
+    if (s == "pp"){ *p = S.pbuf[h->cur^1]; *bytes = B*N*n*4; return true; }
+    auto it = h->arrays.find(s);
+    if (it == h->arrays.end()){ return false; }
+    *p = it->second.first; *bytes = it->second.second; return true;
+}
+extern "C" int pddp_set_array(pddp_handle h, const char *name, const void *src, long nbytes){
+    if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    if (!resolve(h, name, &p, &bytes) || (size_t)nbytes != bytes){ h->err = std::string("bad array name/size: ") + name; return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device)); CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return 0;
+}
+extern "C" int pddp_get_array(pddp_handle h, const char *name, void *dst, long nbytes){
+    if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    if (!resolve(h, name, &p, &bytes) || (size_t)nbytes != bytes){ h->err = std::string("bad array name/size: ") + name; return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device)); CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost)); return 0;
+}
+template <typename F>
+static int timed_phase(pddp_handle h, F f){
+    CK(cudaSetDevice(h->cfg.device));
+    long l0 = h->launches;
+    CK(cudaEventRecord(h->ev[4], h->stream));
+    int rc = f(); if (rc){ return rc; }
+    CK(cudaEventRecord(h->ev[5], h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->last_ms = ms; h->last_launches = (int)(h->launches - l0);
+    return 0;
+}
+extern "C" int pddp_phase_load_init(pddp_handle h, const float *x0, const float *u0, const float *xGoal, int ignoreFirstDefectFlag){
+    if (!h){ return PDDP_E_INVALID; }
+    DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m;
+    return timed_phase(h, [&](){
+        int rc = launch_reset(h, ignoreFirstDefectFlag); if (rc){ return rc; }
+        CK(cudaMemcpyAsync(S.xp, x0, B*N*n*4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(S.up, u0, B*N*m*4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(S.xGoal, xGoal, B*n*4, cudaMemcpyHostToDevice, h->stream));
+        return launch_init(h);
+    });
+}
+extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_bp(h); }); }
+extern "C" int pddp_phase_forward_sweep(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sweep(h); }); }
+extern "C" int pddp_phase_forward_sim(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sim(h); }); }
+extern "C" int pddp_phase_line_search(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_select(h); }); }
+extern "C" int pddp_phase_next_iteration(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_nis(h); }); }
+extern "C" int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches){
+    if (!h){ return PDDP_E_INVALID; } if (ms){ *ms = h->last_ms; } if (launches){ *launches = h->last_launches; } return 0;
+}
