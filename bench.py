@@ -1,0 +1,238 @@
+#!/usr/bin/env python3
+"""bench.py -- iLQR iterations/sec of the batched hot path on N B200s (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch: pddp_solve of 64 Kuka problems (N=128 knots, 16 alphas, M=4,
+TOL_COST=0 so every problem runs MAX_ITER=100 iterations) = 6400 iLQR iterations per GPU per step.
+
+  value  : whole-job iterations/s with the inputs already resident in HBM (pddp_solve_device), device time from CUDA
+           events recorded by the library on ITS launch stream, max over ranks
+  e2e    : the same metric through the reference-facing C-ABI call pddp_solve with HOST buffers (H2D of x0,u0,xGoal and
+           D2H of x,u,Jout,alphaOut,iters inside the timed region), wall clock around the call, max over ranks
+  roofline: the backward-pass kernel (the metric's kernel): algorithmic bytes (656 452 B per problem per
+           backward pass at N=128,M=4) x problems per launch / its mean launch duration, against MEASURED_PEAKS.json
+  cpu_baseline: the UNMODIFIED reference's CPU path (oracle/_ref, runiLQR_CPU2 = parallel line search) on a bounded sample
+
+`--impl reference` times that CPU path alone (rank 0 only).  Multi-GPU: problems are independent, so ranks shard the
+global batch (64 per rank, weak scaling) with no data-path collective; iteration counts are all-gathered at the end."""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_KNOTS, N_ALPHA, M_BLOCKS, BATCH_PER_GPU, MAX_ITER = 128, 16, 4, 64, 100
+BP_BYTES_PER_PROBLEM = 4 * ((N_KNOTS - 1) * 1281 + 4 * 238 + 3 * 14 + 2 * 210 + 3 * 4)   # = 656452
+METRIC = "ilqr_iterations_per_sec"
+UNIT = "iterations/s"
+CONFIG = {"workload": "configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batch=64 per GPU, TOL_COST=0 (100 iterations per problem)",
+          "plant": "kuka_iiwa14", "knots": N_KNOTS, "n_alpha": N_ALPHA, "m_blocks": M_BLOCKS, "batch_per_gpu": BATCH_PER_GPU,
+          "max_iter": MAX_ITER, "l2": "a 256 MiB buffer is rewritten between timed steps (working set 69 MB < 126 MB L2)"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def ref_cpu_run(nseeds, mode="P", seed0=0):
+    """Unmodified reference CPU path on `nseeds` benchmark problems; returns (iters_per_sec, total_iters, seconds, cores) or None."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_driver_N{N_KNOTS}")
+    if not os.path.exists(exe):
+        return None
+    r = subprocess.run([exe, "time", mode, str(seed0), str(nseeds), "0.0"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    m = re.search(r"REFSUMMARY (\{.*\})", r.stderr)
+    if not m:
+        return None
+    s = json.loads(m.group(1))
+    return s["total_iters"] / (s["sum_solve_ms"] / 1000.0), s["total_iters"], s["sum_solve_ms"] / 1000.0, s["cores"]
+
+
+def oracle_port_run(nprob):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    pddp = importlib.import_module("parallel-ddp_b200")
+    x0, u0, xg = pddp.make_inputs_kuka(N_KNOTS, nprob, 0)
+    L = ol.lib(True); cfg = ol.kuka_cfg(N_KNOTS, fma=True); cp = C.byref(cfg)
+    t0 = time.time(); tot = 0
+    for b in range(nprob):
+        ox = np.zeros((N_KNOTS, 14), np.float32); ou = np.zeros((N_KNOTS, 7), np.float32)
+        oJ = np.zeros(MAX_ITER + 1, np.float32); oa = np.zeros(MAX_ITER + 1, np.int32)
+        tot += L.orc_solve(cp, ol.fptr(x0[b]), ol.fptr(u0[b]), ol.fptr(xg[b]), ol.fptr(ox), ol.fptr(ou), ol.fptr(oJ), ol.iptr(oa))
+    dt = time.time() - t0
+    return tot / dt, tot, dt, 1
+
+
+def cpu_baseline(nseeds=8):
+    r = ref_cpu_run(nseeds)
+    if r:
+        return {"value": r[0], "unit": UNIT, "cores": r[3], "kind": "reference",
+                "sample": f"{nseeds} of the 64 benchmark problems (seeds 0..{nseeds-1}) x 100 iterations, reference runiLQR_CPU2 (std::thread parallel line search), {r[2]:.1f} s"}
+    r = oracle_port_run(2)
+    return {"value": r[0], "unit": UNIT, "cores": 1, "kind": "port", "sample": f"2 benchmark problems x 100 iterations, single-threaded oracle port, {r[2]:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    per_step = 2
+    for _ in range(min(args.warmup, 1)):
+        ref_cpu_run(1)
+    tot_it, tot_s, cores, kind = 0, 0.0, 1, "reference"
+    for s in range(args.steps):
+        r = ref_cpu_run(per_step, seed0=(s * per_step) % 64)
+        if r is None:
+            r = oracle_port_run(1); kind = "port"
+        tot_it += r[1]; tot_s += r[2]; cores = r[3]
+    v = tot_it / tot_s
+    sample = f"{per_step} benchmark problems x 100 iterations per step, {args.steps} steps"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1000.0 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": CONFIG,
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pddp = importlib.import_module("parallel-ddp_b200")
+    B, N, L1 = BATCH_PER_GPU, N_KNOTS, MAX_ITER + 1
+    cfg = pddp.default_config_kuka(N, B, device=local_rank, tol_cost=0.0)
+    solver = pddp.Solver(cfg)
+    # this rank's shard of the global batch: problems rank*B .. rank*B+B-1 (seed = problem index)
+    x0, u0, xg = pddp.make_inputs_kuka(N, B, seed0=rank * B)
+    dev = torch.device("cuda", local_rank)
+    d_x0 = torch.from_numpy(x0).to(dev); d_u0 = torch.from_numpy(u0).to(dev); d_xg = torch.from_numpy(xg).to(dev)
+    d_x = torch.empty_like(d_x0); d_u = torch.empty_like(d_u0)
+    d_J = torch.empty((B, L1), dtype=torch.float32, device=dev); d_a = torch.empty((B, L1), dtype=torch.int32, device=dev); d_it = torch.empty(B, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    times = np.zeros(6, np.float64)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        flush.fill_(1); torch.cuda.synchronize()
+        solver.solve_device(d_x0.data_ptr(), d_u0.data_ptr(), d_xg.data_ptr(), d_x.data_ptr(), d_u.data_ptr(), d_J.data_ptr(), d_a.data_ptr(), d_it.data_ptr(), 1, times)
+        return times.copy()
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    t_wall0 = time.time(); dev_ms = 0.0; phase = np.zeros(6)
+    for _ in range(args.steps):
+        t = step_device(); dev_ms += t[0]; phase += t
+    barrier()
+    wall_s = time.time() - t_wall0
+    launches = solver.launch_count() * args.steps
+    iters_rank = int(d_it.sum().item()) * args.steps
+    # end-to-end through the reference-facing call with host buffers
+    for _ in range(min(args.warmup, 2)):
+        solver.runiLQR_GPU(x0, u0, xg)
+    barrier()
+    t0 = time.time(); e2e_iters = 0
+    for _ in range(args.steps):
+        flush.fill_(1); torch.cuda.synchronize()
+        o = solver.runiLQR_GPU(x0, u0, xg); e2e_iters += int(o["iters"].sum())
+    barrier()
+    e2e_s = time.time() - t0
+    clocks = sampler.stop()
+    h2d = x0.nbytes + u0.nbytes + xg.nbytes
+    d2h = o["x"].nbytes + o["u"].nbytes + o["Jout"].nbytes + o["alphaOut"].nbytes + o["iters"].nbytes
+    stats = torch.tensor([dev_ms, e2e_s, float(iters_rank), float(e2e_iters), phase[3]], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, bp_ms = mx[0].item(), mx[1].item(), mx[4].item()
+        iters_all, e2e_iters_all = sm[2].item(), sm[3].item()
+        its = [torch.empty_like(d_it) for _ in range(world)]; dist.all_gather(its, d_it)      # result hand-off (iteration counters) over NVLink
+    else:
+        iters_all, e2e_iters_all, bp_ms = float(iters_rank), float(e2e_iters), phase[3]
+    if rank == 0:
+        value = iters_all / (dev_ms / 1000.0)
+        bp_launches = MAX_ITER * args.steps
+        bp_avg_s = (bp_ms / 1000.0) / bp_launches
+        peak, peak_src = peaks()
+        achieved = B * BP_BYTES_PER_PROBLEM / bp_avg_s / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": dict(CONFIG, global_batch=B * world, parallelism=f"problem-sharded x{world}"),
+               "e2e": {"value": e2e_iters_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": launches, "clocks": clocks,
+               "roofline": {"kernel": "bp_kernel<14,7>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src, "avg_launch_us": bp_avg_s * 1e6, "problems_per_launch": B,
+                            "algorithmic_bytes_per_problem": BP_BYTES_PER_PROBLEM},
+               "phases_ms_per_step": {k: float(v) / args.steps for k, v in zip(("total", "sim+select", "sweep", "bp", "nis", "init+store"), phase)},
+               "wall_s_device_leg": wall_s}
+        ncu = os.path.join(ROOT, "profiles", "bp_traffic.json")
+        if os.path.exists(ncu):
+            out["roofline"]["traffic"] = json.load(open(ncu)).get("dram_bytes_per_launch")
+        if world == 1:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

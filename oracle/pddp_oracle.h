@@ -69,6 +69,7 @@ void  orc_ws_free(orc_ws *w);
 /* plant plug-ins (Kuka) */
 void  orc_kuka_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd);                  /* dynamics_arm.cuh:2095-2163 */
 void  orc_kuka_dynamics_gradient(const orc_cfg *c, const float *x, const float *u, float *qdd, float *dqdd /*[147]*/); /* :2165-2289 */
+int   orc_kuka_gradient_stages(const orc_cfg *c, const float *x, const float *u, float *stages);          /* debug dump, returns float count */
 /* generic plant dispatch */
 void  orc_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd);
 void  orc_integrator(const orc_cfg *c, const float *x, const float *u, float *xnext);                 /* integrators.cuh */
