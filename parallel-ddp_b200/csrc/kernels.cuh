@@ -56,7 +56,12 @@ template <int N_> __device__ __forceinline__ void cp_async_wait(){ asm volatile(
 // ------------------------------------------------------------------------------------------------------------------
 // backward pass
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int BP_THREADS = 128;
+// One CTA of BP_THREADS (16 warps) per (problem, time block).  Every knot is five barrier-separated stages; inside a
+// stage each thread owns at most one output element (a 14- or 7-term fused chain), its indices fixed before the knot
+// loop.  The 7x7 Huu inverse is the serial bottleneck of a knot, so warp 0 computes Huu first and eliminates it in
+// registers (shuffles) while warps 1..15 assemble the other 392 entries of H and g.  The inputs of knot k-1 (AB, H, g,
+// d: 3.1 KB) are in flight (LDGSTS) while knot k is processed.
+constexpr int BP_THREADS = 512;
 template <int n, int m>
 struct BpSmem {
     static constexpr int nm = n + m;
@@ -70,22 +75,24 @@ struct BpSmem {
     float K[m*n], du[m];
     float Huu[2*m*m];
     float dx[n];
+    float dJ[2*m];
 };
 
 template <int n, int m>
 __device__ __forceinline__ void bp_prefetch(BpSmem<n,m> &s, int buf, const float *gAB, const float *gH, const float *gg, const float *gd){
     constexpr int nm = n + m;
-    for (int i = threadIdx.x; i < n*nm; i += BP_THREADS){ cp_async4(&s.AB[buf][i], gAB + i); }
-    for (int i = threadIdx.x; i < nm*nm; i += BP_THREADS){ cp_async4(&s.Hc[buf][i], gH + i); }
-    if (threadIdx.x < nm){ cp_async4(&s.gc[buf][threadIdx.x], gg + threadIdx.x); }
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + n){ cp_async4(&s.dk[buf][threadIdx.x-32], gd + threadIdx.x - 32); }
+    const int t = threadIdx.x;
+    if (t < n*nm){ cp_async4(&s.AB[buf][t], gAB + t); }
+    if (t < nm*nm){ cp_async4(&s.Hc[buf][t], gH + t); }
+    if (t >= nm*nm && t < nm*nm + nm){ cp_async4(&s.gc[buf][t - nm*nm], gg + t - nm*nm); }
+    if (t >= nm*nm + nm && t < nm*nm + nm + n){ cp_async4(&s.dk[buf][t - nm*nm - nm], gd + t - nm*nm - nm); }
     cp_async_commit();
 }
 
-// grid = B*M CTAs of BP_THREADS; CTA (b, block) walks its N/M knots backwards.
 template <int n, int m>
 __global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur){
     constexpr int nm = n + m, oHXU = n*nm, oHUU = n*nm + n, oGU = n, oB = n*n;
+    static_assert(nm*nm + nm + n <= BP_THREADS && n*nm + n <= BP_THREADS, "one element per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BpSmem<n,m> &s = *reinterpret_cast<BpSmem<n,m>*>(smem_raw);
     const int b = blockIdx.x / S.M, block = blockIdx.x % S.M, t = threadIdx.x;
@@ -98,19 +105,38 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur){
     const float *gd = S.dp + (size_t)b*N*n, *gx = S.xp + (size_t)b*N*n, *gx2 = S.xp2 + (size_t)b*N*n;
     float *gKT = S.KT + (size_t)b*N*n*m, *gdu = S.du + (size_t)b*N*m, *gApBK = S.ApBK + (size_t)b*N*n*n, *gBdu = S.Bdu + (size_t)b*N*n;
 
+    // ---- per-thread roles, fixed for the whole block of knots
+    // stage A: element t of AB2 (t < n*nm); threads n*nm .. n*nm+n-1 update p
+    const int a_ky = t / nm, a_kx = t % nm;
+    // stage B: warp 0 -> Huu (2 per lane) then the elimination; threads 32.. -> the other H entries, then g
+    int b_kx = -1, b_ky = 0;
+    {
+        const int item = t - 32;
+        if (item >= 0 && item < n*nm){ b_ky = item / nm; b_kx = item % nm; }                               // columns 0..n-1, all rows
+        else if (item >= n*nm && item < n*nm + m*n){ const int q = item - n*nm; b_ky = n + q / n; b_kx = q % n; } // columns n.., rows 0..n-1
+    }
+    const int b_g = (t - 32 - (nm*nm - m*m));          // 0..nm-1 -> g
+    // stage C: K element t (t < n*m): kx = row of K (m), ky = column (n); threads 128.. -> du
+    const int c_ky = t / m, c_kx = t % m;
+    // stage D: [0, n*m) T;  [128, 128+n*n) ApBK;  [352, 352+n) Bdu;  [384, 384+m) expected reduction;  [400, 400+n*m) KT store; [500,500+m) du store
+    const int d_ky = t / n, d_kx = t % n;                       // T (ky < m) and KT store
+    const int d2 = t - 128, d2_ky = d2 / n, d2_kx = d2 % n;     // ApBK
+    // stage E: P element t (t < n*n); threads 256.. -> p
+    const int e_ky = t / n, e_kx = t % n;
+
     int ks = NBB*(block+1) - 1, iterCount;
-    float dJ0 = 0.f, dJ1 = 0.f;          // thread ind < m: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
+    float dJ0 = 0.f, dJ1 = 0.f;          // thread 384+ind: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
     if (ks == N - 1){
         // final block: Hxx[N-1] -> P[N-2], gx[N-1] -> p[N-2]  (bpHelpers.cuh:362-367)
-        for (int i = t; i < n*n; i += BP_THREADS){ int kx = i % n, ky = i / n; float v = MUL(1.0f, gH[(size_t)ks*nm*nm + kx + nm*ky]); s.P[i] = v; gP[(size_t)(ks-1)*n*n + i] = v; }
-        if (t < n){ float v = MUL(1.0f, gg[ks*nm + t]); s.p[t] = v; gp[(ks-1)*n + t] = v; }
+        if (t < n*n){ const int kx = t % n, ky = t / n; float v = MUL(1.0f, gH[(size_t)ks*nm*nm + kx + nm*ky]); s.P[t] = v; gP[(size_t)(ks-1)*n*n + t] = v; }
+        if (t >= 256 && t < 256 + n){ const int r = t - 256; float v = MUL(1.0f, gg[ks*nm + r]); s.p[r] = v; gp[(ks-1)*n + r] = v; }
         ks--; iterCount = NBB - 2;
         __syncthreads();
     } else {
         // other blocks: start from the previous iteration's P,p at the block boundary, shifted to the new linearisation point
         iterCount = NBB - 1;
-        for (int i = t; i < n*n; i += BP_THREADS){ s.P[i] = gPp[(size_t)ks*n*n + i]; }
-        if (t < n){ s.dx[t] = SUB(gx[(ks+1)*n + t], gx2[(ks+1)*n + t]); }
+        if (t < n*n){ s.P[t] = gPp[(size_t)ks*n*n + t]; }
+        if (t >= 256 && t < 256 + n){ const int r = t - 256; s.dx[r] = SUB(gx[(ks+1)*n + r], gx2[(ks+1)*n + r]); }
         __syncthreads();
         if (t < n){
             float val = 0.f;
@@ -122,134 +148,143 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur){
     }
     bp_prefetch<n,m>(s, 0, gAB + (size_t)ks*n*nm, gH + (size_t)ks*nm*nm, gg + ks*nm, gd + ks*n);
     int buf = 0;
+    #pragma unroll 1
     for (int iter = iterCount; iter >= 0; iter--, ks--, buf ^= 1){
         if (iter > 0){ bp_prefetch<n,m>(s, buf^1, gAB + (size_t)(ks-1)*n*nm, gH + (size_t)(ks-1)*nm*nm, gg + (ks-1)*nm, gd + (ks-1)*n); cp_async_wait<1>(); }
         else { cp_async_wait<0>(); }
         __syncthreads();
         const float *sAB = s.AB[buf], *bH = s.Hc[buf], *bg = s.gc[buf], *bd = s.dk[buf];
-        // ---- backprop: AB2 = AB'(P + rho I[u rows]);  p += P d on the block-local defect boundary
-        for (int e = t; e < n*nm; e += BP_THREADS){
-            int ky = e / nm, kx = e % nm; float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(sAB[kx*n+j], ADD(s.P[ky*n+j], (kx >= n && ky == j) ? rho : 0.f), val); }
-            s.AB2[ky*nm+kx] = val;
-        }
-        float pnew = 0.f;
-        if (t < n){
+        // ---- stage A: AB2 = AB'(P + rho I[u rows]);  p += P d on the block-local defect boundary (bpHelpers.cuh:54-81)
+        if (t < n*nm){
             float val = 0.f;
+            #pragma unroll
+            for (int j = 0; j < n; j++){ val = FMA(sAB[a_kx*n+j], ADD(s.P[a_ky*n+j], (a_kx >= n && a_ky == j) ? rho : 0.f), val); }
+            s.AB2[a_ky*nm+a_kx] = val;
+        } else if (t < n*nm + n){
+            const int r = t - n*nm; float val = 0.f;
             if (S.M > 1 && (((iter+1) % NBB) == 0) && iter < N-1){
                 #pragma unroll
-                for (int j = 0; j < n; j++){ val = FMA(bd[j], ADD(s.P[t + j*n], 0.f), val); }
+                for (int j = 0; j < n; j++){ val = FMA(bd[j], ADD(s.P[r + j*n], 0.f), val); }
             }
-            pnew = ADD(s.p[t], val);
+            s.p[r] = ADD(s.p[r], val);
         }
         __syncthreads();
-        if (t < n){ s.p[t] = pnew; }
-        // ---- H = (AB2 AB)' + H_cost
-        for (int e = t; e < nm*nm; e += BP_THREADS){
-            int ky = e / nm, kx = e % nm; float val = 0.f;
+        // ---- stage B: H = (AB2 AB)' + H_cost, g = AB'p + g_cost; warp 0 does Huu first and inverts it meanwhile
+        if (t < 32){
             #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(s.AB2[ky+nm*j], sAB[kx*n+j], val); }
-            s.H[kx+nm*ky] = FMA(1.0f, val, MUL(1.0f, bH[kx+nm*ky]));
+            for (int q = 0; q < 2; q++){
+                const int e = t + 32*q;
+                if (e < m*m){
+                    const int ky = n + e / m, kx = n + e % m; float val = 0.f;
+                    #pragma unroll
+                    for (int j = 0; j < n; j++){ val = FMA(s.AB2[ky+nm*j], sAB[kx*n+j], val); }
+                    const float h = FMA(1.0f, val, MUL(1.0f, bH[kx+nm*ky]));
+                    s.H[kx+nm*ky] = h;
+                    s.Huu[(kx-n) + m*(ky-n)] = MUL(1.0f, h); s.Huu[m*m + (ky-n)*m + (kx-n)] = (kx == ky) ? 1.f : 0.f;
+                }
+            }
+            __syncwarp();
+            gauss_jordan_warp_reg<m>(s.Huu);
+        } else {
+            if (b_kx >= 0){
+                float val = 0.f;
+                #pragma unroll
+                for (int j = 0; j < n; j++){ val = FMA(s.AB2[b_ky+nm*j], sAB[b_kx*n+j], val); }
+                s.H[b_kx+nm*b_ky] = FMA(1.0f, val, MUL(1.0f, bH[b_kx+nm*b_ky]));
+            } else if (b_g >= 0 && b_g < nm){
+                float val = 0.f;
+                #pragma unroll
+                for (int j = 0; j < n; j++){ val = FMA(s.p[j], sAB[b_g*n+j], val); }
+                s.g[b_g] = FMA(1.0f, val, MUL(1.0f, bg[b_g]));
+            }
         }
-        __syncthreads();   // p visible
-        // ---- g = AB'p + g_cost
-        if (t < nm){
-            float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(s.p[j], sAB[t*n+j], val); }
-            s.g[t] = FMA(1.0f, val, MUL(1.0f, bg[t]));
-        }
-        // ---- [Huu | I]
-        for (int e = t; e < m*m; e += BP_THREADS){ int ky = e / m, kx = e % m; s.Huu[kx+m*ky] = MUL(1.0f, s.H[oHUU+kx+nm*ky]); s.Huu[m*m+ky*m+kx] = (kx == ky) ? 1.f : 0.f; }
-        __syncthreads();
-        if (t < 32){ gauss_jordan_warp<m>(s.Huu); }
         __syncthreads();
         const float *Hinv = &s.Huu[m*m];
-        // ---- K = Huu^-1 Hux, du = Huu^-1 gu
-        for (int e = t; e < n*m; e += BP_THREADS){
-            int ky = e / m, kx = e % m; float val = 0.f;
+        // ---- stage C: K = Huu^-1 Hux, du = Huu^-1 gu (bpHelpers.cuh:206-220)
+        if (t < n*m){
+            float val = 0.f;
             #pragma unroll
-            for (int j = 0; j < m; j++){ val = FMA(Hinv[kx+m*j], s.H[oGU + ky*nm + j], val); }
-            s.K[kx+ky*m] = MUL(1.0f, val);
-        }
-        if (t >= 96 && t < 96 + m){
-            int r = t - 96; float val = 0.f;
+            for (int j = 0; j < m; j++){ val = FMA(Hinv[c_kx+m*j], s.H[oGU + c_ky*nm + j], val); }
+            s.K[c_kx+c_ky*m] = MUL(1.0f, val);
+        } else if (t >= 128 && t < 128 + m){
+            const int r = t - 128; float val = 0.f;
             #pragma unroll
             for (int j = 0; j < m; j++){ val = FMA(Hinv[r+m*j], s.g[oGU+j], val); }
             s.du[r] = ADD(MUL(1.0f, val), 0.f);
         }
         __syncthreads();
-        // ---- outputs KT, du; T = K'Huu - Hxu (into AB2); forward-sweep operators; expected reduction
-        for (int e = t; e < n*m; e += BP_THREADS){ int ky = e / n, kx = e % n; gKT[(size_t)ks*n*m + kx + n*ky] = s.K[ky + m*kx]; }
-        if (t < m){ gdu[ks*m + t] = s.du[t]; }
+        // ---- stage D: T = K'Huu - Hxu (into AB2), A-BK, B du, expected reduction, KT/du to HBM
         const bool do_ctg = (iter != 0 || block != 0);
-        if (do_ctg){
-            for (int e = t; e < n*m; e += BP_THREADS){
-                int ky = e / n, kx = e % n; float val = 0.f;
+        if (t < n*m){
+            if (do_ctg){
+                float val = 0.f;
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = FMA(s.K[kx*m+j], s.H[oHUU+ky*nm+j], val); }
-                s.AB2[kx+ky*n] = SUB(val, s.H[oHXU+kx+nm*ky]);
+                for (int j = 0; j < m; j++){ val = FMA(s.K[d_kx*m+j], s.H[oHUU+d_ky*nm+j], val); }
+                s.AB2[d_kx+d_ky*n] = SUB(val, s.H[oHXU+d_kx+nm*d_ky]);
             }
-        }
-        if (S.M > 1){
-            for (int e = t; e < n*n; e += BP_THREADS){
-                int ky = e / n, kx = e % n; float val = 0.f;
+        } else if (t >= 128 && t < 128 + n*n){
+            if (S.M > 1){
+                float val = 0.f;
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = FMA(sAB[oB+kx+n*j], s.K[ky*m+j], val); }
-                gApBK[(size_t)ks*n*n + kx + n*ky] = SUB(sAB[kx+n*ky], val);
+                for (int j = 0; j < m; j++){ val = FMA(sAB[oB+d2_kx+n*j], s.K[d2_ky*m+j], val); }
+                gApBK[(size_t)ks*n*n + d2_kx + n*d2_ky] = SUB(sAB[d2_kx+n*d2_ky], val);
             }
-            if (t >= 64 && t < 64 + n){
-                int kx = t - 64; float val = 0.f;
+        } else if (t >= 352 && t < 352 + n){
+            if (S.M > 1){
+                const int kx = t - 352; float val = 0.f;
                 #pragma unroll
                 for (int j = 0; j < m; j++){ val = FMA(sAB[oB+kx+n*j], s.du[j], val); }
                 gBdu[ks*n + kx] = val;
             }
-        }
-        if (t >= 32 && t < 32 + m){
-            int ind = t - 32; float dot = 0.f;
+        } else if (t >= 384 && t < 384 + m){
+            const int ind = t - 384; float dot = 0.f;
             #pragma unroll
             for (int j = 0; j < m; j++){ dot = FMA(s.H[oHUU+ind+nm*j], s.du[j], dot); }
             dJ0 = FMA(s.du[ind], s.g[oGU+ind], dJ0); dJ1 = FMA(s.du[ind], dot, dJ1);
+        } else if (t >= 400 && t < 400 + n*m){
+            const int e = t - 400, ky = e / n, kx = e % n;
+            gKT[(size_t)ks*n*m + kx + n*ky] = s.K[ky + m*kx];
+        } else if (t >= 500 && t < 500 + m){
+            gdu[ks*m + t - 500] = s.du[t - 500];
         }
         __syncthreads();
-        // ---- cost-to-go of the previous knot
+        // ---- stage E: cost-to-go of the previous knot (bpHelpers.cuh:223-276)
         if (do_ctg){
-            for (int e = t; e < n*n; e += BP_THREADS){
-                int ky = e / n, kx = e % n; float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.AB2[kx+n*j], s.K[ky*m+j], -MUL(s.K[kx*m+j], s.H[oGU+ky*nm+j]))); }
-                float v = ADD(s.H[kx+ky*nm], val);
-                s.P[kx+ky*n] = v; gP[(size_t)(ks-1)*n*n + kx + ky*n] = v;
-            }
-            if (t < n){
+            if (t < n*n){
                 float val = 0.f;
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], s.AB2[t+n*j], -MUL(s.K[t*m+j], s.g[oGU+j]))); }
-                float v = ADD(s.g[t], val);
-                s.p[t] = v; gp[(ks-1)*n + t] = v;
+                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.AB2[e_kx+n*j], s.K[e_ky*m+j], -MUL(s.K[e_kx*m+j], s.H[oGU+e_ky*nm+j]))); }
+                const float v = ADD(s.H[e_kx+e_ky*nm], val);
+                s.P[t] = v; gP[(size_t)(ks-1)*n*n + t] = v;
+            } else if (t >= 256 && t < 256 + n){
+                const int r = t - 256; float val = 0.f;
+                #pragma unroll
+                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], s.AB2[r+n*j], -MUL(s.K[r*m+j], s.g[oGU+j]))); }
+                const float v = ADD(s.g[r], val);
+                s.p[r] = v; gp[(ks-1)*n + r] = v;
             }
         }
-        __syncthreads();
+        // the next iteration's top-of-loop barrier orders stage E's writes before stage A's reads
     }
     // ---- expected cost reduction of this block: thread 0 sums the m per-thread partials in order (bpHelpers.cuh:416)
-    if (t >= 32 && t < 32 + m){ s.AB2[t-32] = dJ0; s.AB2[m + t-32] = dJ1; }
+    if (t >= 384 && t < 384 + m){ s.dJ[t-384] = dJ0; s.dJ[m + t-384] = dJ1; }
     __syncthreads();
     if (t == 0){
-        float a0 = s.AB2[0], a1 = s.AB2[m];
-        for (int j = 1; j < m; j++){ a0 = ADD(a0, s.AB2[j]); a1 = ADD(a1, s.AB2[m+j]); }
+        float a0 = s.dJ[0], a1 = s.dJ[m];
+        for (int j = 1; j < m; j++){ a0 = ADD(a0, s.dJ[j]); a1 = ADD(a1, s.dJ[m+j]); }
         S.dJexp[(size_t)b*2*S.M + 2*block] = a0; S.dJexp[(size_t)b*2*S.M + 2*block + 1] = a1;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward sweep: x_a[k+1] = xp[k+1] + ( -alpha_a Bdu_k + (A-BK)_k (x_a[k]-xp[k]) + [boundary] d_k )
-// grid = B CTAs of 32*A threads; the whole (A-BK) sequence of the problem is staged in shared memory once.
+// grid = B*splits CTAs of 32*A/splits threads; the whole (A-BK) sequence of the problem is staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------------------
 template <int n>
-__global__ void sweep_kernel(DevState S){
+__global__ void sweep_kernel(DevState S, int splits){
     extern __shared__ __align__(16) float sw[];
-    const int b = blockIdx.x, N = S.N, NBF = N / S.M;
+    // `splits` CTAs share one problem (each takes A/splits step sizes) so that a small batch still covers the SMs
+    const int b = blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
     if (S.done[b]){ return; }
     float *sA = sw;                         // [N-1][n*n]
     float *sB = sA + (size_t)(N-1)*n*n;     // [N-1][n]
@@ -263,7 +298,7 @@ __global__ void sweep_kernel(DevState S){
         for (int i = threadIdx.x; i < N*n; i += blockDim.x){ sxp[i] = gxp[i]; sd[i] = gd[i]; }
     }
     __syncthreads();
-    const int a = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;
     if (a >= S.A){ return; }
     const float alpha = S.alpha[a];
     float *gx = S.x + ((size_t)b*S.A + a)*N*n;

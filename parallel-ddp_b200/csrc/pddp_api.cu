@@ -25,7 +25,7 @@ struct pddp_solver {
     std::string err;
     int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
     long launches = 0;
-    int n, m;
+    int n, m, num_sms = 148;
     float *d_xout = nullptr, *d_uout = nullptr; int *d_iters = nullptr;
     float *h_stage = nullptr; size_t h_stage_bytes = 0;    // pinned staging
     int *h_nactive = nullptr;
@@ -75,6 +75,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     auto bail = [&](int code){ g_create_error = h->err; for (void *p : h->allocs){ cudaFree(p); } delete h; return code; };
     #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess){ h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(PDDP_E_CUDA); } } while (0)
     CKC(cudaSetDevice(cfg->device));
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sms > 0){ h->num_sms = sms; } }
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev){ CKC(cudaEventCreate(&e)); }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S));
@@ -182,7 +183,9 @@ static int launch_bp(pddp_handle h){
 }
 static int launch_sweep(pddp_handle h){
     DevState &S = h->S; if (S.M == 1){ return 0; }
-    sweep_kernel<kuka::NX><<<S.B, 32*S.A, h->smem_sweep, h->stream>>>(S);
+    // enough CTAs to cover the SMs: split the step sizes of one problem over up to A CTAs (power-of-two divisor of A)
+    int splits = 1; while (S.B*splits*2 <= h->num_sms && (S.A % (splits*2)) == 0){ splits *= 2; }
+    sweep_kernel<kuka::NX><<<S.B*splits, 32*(S.A/splits), h->smem_sweep, h->stream>>>(S, splits);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_sim(pddp_handle h){
