@@ -321,9 +321,11 @@ __global__ void sweep_kernel(DevState S, int splits){
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward simulation + per-knot cost + defects
-// grid = B*A CTAs of 32*M threads: warp w simulates shooting interval w of candidate (b, a).
+// grid = B*A/2 CTAs of 32*M threads: warp w simulates shooting interval w of TWO candidates (b, a) and (b, a+1), one per
+// half-warp (SIM_LANES = 16 lanes cooperate on one trajectory; both halves run the same instruction stream).
 // ------------------------------------------------------------------------------------------------------------------
-struct SimWarpSmem {
+constexpr int SIM_LANES = 16;
+struct SimGroupSmem {
     kuka::FwdWs ws;
     float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
 };
@@ -342,19 +344,24 @@ __device__ __forceinline__ float cost_knot(const float *x, const float *u, const
 
 __global__ void sim_kernel(DevState S){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, m = kuka::NU;
+    constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES, GPW = 32 / SIM_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw);            // 252
     float *sTb = sI + 36*kuka::NB;                             // 252
     float *sxg = sTb + 36*kuka::NB;                            // 16
-    SimWarpSmem *wsm = reinterpret_cast<SimWarpSmem*>(sxg + 16);
-    const int b = blockIdx.x / S.A, a = blockIdx.x % S.A;
+    SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sxg + 16);
+    const int apb = (S.A + GPW - 1) / GPW;                     // CTAs per problem
+    const int b = blockIdx.x / apb;
     if (S.done[b]){ return; }
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
     if (threadIdx.x < n){ sxg[threadIdx.x] = S.xGoal[b*n + threadIdx.x]; }
     __syncthreads();
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     if (w >= S.M){ return; }
-    SimWarpSmem &s = wsm[w];
+    int a = (blockIdx.x % apb)*GPW + grp;
+    const bool live = a < S.A;                                 // odd A: the last half-warp replays candidate A-1 without storing
+    if (!live){ a = S.A - 1; }
+    SimGroupSmem &s = gsm[w*GPW + grp];
+    kuka::init_ws<LANES>(s.ws, nullptr, sTb);
     const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (w < S.M - 1) ? NBF : NBF - 1;
     const float alpha = S.alpha[a], dt = S.dt;
     float *gx = S.x + ((size_t)b*S.A + a)*N*n, *gu = S.u + ((size_t)b*S.A + a)*N*m, *gdd = S.d + ((size_t)b*S.A + a)*N*n;
@@ -363,22 +370,24 @@ __global__ void sim_kernel(DevState S){
     // state at the start of the interval (left there by the sweep)
     if (l < n){ s.x[l] = gx[kStart*n + l]; }
     // prefetch registers for knot kStart
-    float rKT[4], rdu = 0.f, rxp = 0.f, rup = 0.f;
+    constexpr int KTQ = (n*m + LANES - 1) / LANES;
+    float rKT[KTQ], rdu = 0.f, rxp = 0.f, rup = 0.f;
     #pragma unroll
-    for (int q = 0; q < 4; q++){ int i = l + 32*q; rKT[q] = (i < n*m) ? gKT[(size_t)kStart*n*m + i] : 0.f; }
+    for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = (i < n*m) ? gKT[(size_t)kStart*n*m + i] : 0.f; }
     if (l < m){ rdu = gdu[kStart*m + l]; rup = gup[kStart*m + l]; }
     if (l < n){ rxp = gxp[kStart*n + l]; }
     __syncwarp();
+    #pragma unroll 1
     for (int kk = 0; kk < iters; kk++){
         const int k = kStart + kk;
         // stage this knot's feedback data, start fetching the next knot's
         #pragma unroll
-        for (int q = 0; q < 4; q++){ int i = l + 32*q; if (i < n*m){ s.KT[i] = rKT[q]; } }
+        for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; if (i < n*m){ s.KT[i] = rKT[q]; } }
         if (l < n){ s.dx[l] = SUB(s.x[l], rxp); }
         const float du_k = rdu, up_k = rup;
         if (kk + 1 < iters){
             #pragma unroll
-            for (int q = 0; q < 4; q++){ int i = l + 32*q; rKT[q] = (i < n*m) ? gKT[(size_t)(k+1)*n*m + i] : 0.f; }
+            for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = (i < n*m) ? gKT[(size_t)(k+1)*n*m + i] : 0.f; }
             if (l < m){ rdu = gdu[(k+1)*m + l]; rup = gup[(k+1)*m + l]; }
             if (l < n){ rxp = gxp[(k+1)*n + l]; }
         }
@@ -388,27 +397,27 @@ __global__ void sim_kernel(DevState S){
             float Kdx = 0.f;
             #pragma unroll
             for (int c = 0; c < n; c++){ Kdx = FMA(s.KT[c + l*n], s.dx[c], Kdx); }
-            float uu = SUB(up_k, FMA(alpha, du_k, Kdx));
-            s.u[l] = uu; gu[k*m + l] = uu;
+            const float uu = SUB(up_k, FMA(alpha, du_k, Kdx));
+            s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
         }
         __syncwarp();
-        // running cost of knot k (one lane; the others are already inside the dynamics)
-        if (l == 31){ gc[k] = cost_knot(s.x, s.u, sxg, false, S); }
-        kuka::forward<false>(s.ws, nullptr, sI, sTb, s.x, s.u, s.qdd);
+        // running cost of knot k (one lane per trajectory)
+        if (l == LANES-1 && live){ gc[k] = cost_knot(s.x, s.u, sxg, false, S); }
+        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd);
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
         __syncwarp();
         if (kk < NBF - 1){
-            if (l < n){ float v = s.xn[l]; s.x[l] = v; gx[(k+1)*n + l] = v; }
+            if (l < n){ const float v = s.xn[l]; s.x[l] = v; if (live){ gx[(k+1)*n + l] = v; } }
         } else if (w < S.M - 1){
             // last step of a non-final interval: defect against the next interval's start state (fpHelpers.cuh:255-258)
-            if (l < n){ gdd[((w+1)*NBF-1)*n + l] = SUB(s.xn[l], gx[(k+1)*n + l]); }
+            if (l < n && live){ gdd[((w+1)*NBF-1)*n + l] = SUB(s.xn[l], gx[(k+1)*n + l]); }
         }
         __syncwarp();
     }
     // final-knot cost belongs to the last interval; u[N-1] is never simulated and stays the accepted one
-    if (w == S.M - 1){
-        if (l == 31){ gc[N-1] = cost_knot(s.x, s.u, sxg, true, S); }
+    if (w == S.M - 1 && live){
+        if (l == LANES-1){ gc[N-1] = cost_knot(s.x, s.u, sxg, true, S); }
         if (l < m){ gu[(N-1)*m + l] = gup[(N-1)*m + l]; }
     }
 }
@@ -497,7 +506,8 @@ __global__ void select_kernel(DevState S, int mode){
 // previous one in xp2, and refreshes AB (analytic Euler gradient), g (and H when write_H) at the accepted trajectory.
 // mode 1 = initialisation: the trajectory is already in xp/up, xp2 <- xp.
 // ------------------------------------------------------------------------------------------------------------------
-struct NisWarpSmem {
+constexpr int NIS_LANES = 32;
+struct NisGroupSmem {
     kuka::FwdWs ws; kuka::GradWs gs;
     float x[16], u[8], qdd[8], dqdd[3*kuka::NB*kuka::NB + 1];
 };
@@ -505,50 +515,54 @@ constexpr int NIS_WARPS = 1;
 
 __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode, int write_H){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, m = kuka::NU, nm = n + m, np = kuka::NB;
+    constexpr int n = kuka::NX, m = kuka::NU, nm = n + m, np = kuka::NB, LANES = NIS_LANES, GPW = 32 / NIS_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-    NisWarpSmem *wsm = reinterpret_cast<NisWarpSmem*>(sTb + 36*kuka::NB);
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int gw = blockIdx.x*NIS_WARPS + w, N = S.N;
-    const int b = gw / N, k = gw % N;
+    NisGroupSmem *gsm = reinterpret_cast<NisGroupSmem*>(sTb + 36*kuka::NB);
+    const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
+    const int gk = (blockIdx.x*NIS_WARPS + w)*GPW + grp, N = S.N;        // N is even: the groups of one warp share the problem
+    const int b = gk / N, k = gk % N;
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
     __syncthreads();
     if (b >= S.B || S.done[b]){ return; }
-    NisWarpSmem &s = wsm[w];
+    NisGroupSmem &s = gsm[w*GPW + grp];
+    kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
     const bool acc = (mode == 0) && S.accepted[b];
     const int a = S.alphaIndex[b];
     const float *cx = S.x + (((size_t)b*S.A + a)*N + k)*n, *cu = S.u + (((size_t)b*S.A + a)*N + k)*m, *cd = S.d + (((size_t)b*S.A + a)*N + k)*n;
     if (l < n){
-        float xold = gxp[l]; gxp2[l] = xold;                       // xp2 <- xp (fpHelpers.cuh:371 / nisInitHelpers.cuh:379)
-        float xv = acc ? cx[l] : xold; s.x[l] = xv;
+        const float xold = gxp[l]; gxp2[l] = xold;                 // xp2 <- xp (fpHelpers.cuh:371 / nisInitHelpers.cuh:379)
+        const float xv = acc ? cx[l] : xold; s.x[l] = xv;
         if (acc){ gxp[l] = xv; gdp[l] = cd[l]; }
     }
-    if (l < m){ float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }
+    if (l < m){ const float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }
     __syncwarp();
     // cost gradient (plants/cost_arm.cuh:156-202)
     const float *xg = S.xGoal + b*n;
     float *gg = S.g + ((size_t)b*N + k)*nm;
     const bool fin = (k == N - 1);
-    if (l < n){ gg[l] = MUL(fin ? (l < np ? S.QF1 : S.QF2) : (l < np ? S.Q1 : S.Q2), SUB(s.x[l], xg[l])); }
-    else if (l < nm){ gg[l] = fin ? 0.f : MUL(S.R, s.u[l-n]); }
+    for (int e = l; e < nm; e += LANES){
+        if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
+        else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
+    }
     if (write_H){
         float *gH = S.H + ((size_t)b*N + k)*nm*nm;
-        for (int e = l; e < nm*nm; e += 32){
-            int i = e / nm, j = e % nm; float v = 0.f;
+        for (int e = l; e < nm*nm; e += LANES){
+            const int i = e / nm, j = e % nm; float v = 0.f;
             if (fin){ if (i < n && j < n){ v = (i != j) ? 0.f : (i < np ? S.QF1 : S.QF2); } }
             else { v = (i != j) ? 0.f : (i < np ? S.Q1 : (i < n ? S.Q2 : S.R)); }
             gH[e] = v;
         }
     }
+    // integrator gradient AB = [I 0] + dt [0 I 0 ; dqdd]   (integrators.cuh:15-17,38-53); the final knot has none
+    // (its group still runs the collective code so that both halves of a warp stay in lockstep, but stores nothing)
+    kuka::gradient<LANES>(s.ws, s.gs, sI, s.x, s.u, s.qdd, s.dqdd);
     if (fin){ return; }
-    // integrator gradient AB = [I 0] + dt [0 I 0 ; dqdd]   (integrators.cuh:15-17,38-53)
-    kuka::gradient(s.ws, s.gs, sI, sTb, s.x, s.u, s.qdd, s.dqdd);
     float *gAB = S.AB + ((size_t)b*N + k)*n*nm;
     const float dt = S.dt;
-    for (int e = l; e < n*nm; e += 32){
-        int ky = e / n, kx = e % n;
-        float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
+    for (int e = l; e < n*nm; e += LANES){
+        const int ky = e / n, kx = e % n;
+        const float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
         gAB[e] = FMA(dt, dxd, (ky == kx) ? 1.f : 0.f);
     }
 }
@@ -565,38 +579,45 @@ __global__ void store_kernel(DevState S, float *x_out, float *u_out, int *iters_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// plug-in unit kernels (one warp per sample)
+// plug-in unit kernels (one group per sample, same group widths as the production kernels)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void unit_dynamics_kernel(const float *I, const float *Tbody, const float *x, const float *u, int nsamp, float *qdd){
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LANES = SIM_LANES, GPW = 32 / SIM_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-    SimWarpSmem &s = *reinterpret_cast<SimWarpSmem*>(sTb + 36*kuka::NB);
-    const int l = threadIdx.x & 31;
+    SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
+    const int grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = I[i]; sTb[i] = Tbody[i]; }
     __syncthreads();
-    for (int k = blockIdx.x; k < nsamp; k += gridDim.x){
+    SimGroupSmem &s = gsm[grp];
+    kuka::init_ws<LANES>(s.ws, nullptr, sTb);
+    for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
+        const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;         // tail: replay the last sample
         if (l < kuka::NX){ s.x[l] = x[k*kuka::NX + l]; } if (l < kuka::NU){ s.u[l] = u[k*kuka::NU + l]; }
         __syncwarp();
-        kuka::forward<false>(s.ws, nullptr, sI, sTb, s.x, s.u, s.qdd);
+        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd);
         if (l < kuka::NB){ qdd[k*kuka::NB + l] = s.qdd[l]; }
         __syncwarp();
     }
 }
 __global__ void unit_gradient_kernel(const float *I, const float *Tbody, const float *x, const float *u, int nsamp, float dt, float *AB, float *qdd){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, nm = kuka::NX + kuka::NU, np = kuka::NB;
+    constexpr int n = kuka::NX, nm = kuka::NX + kuka::NU, np = kuka::NB, LANES = NIS_LANES, GPW = 32 / NIS_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-    NisWarpSmem &s = *reinterpret_cast<NisWarpSmem*>(sTb + 36*kuka::NB);
-    const int l = threadIdx.x & 31;
+    NisGroupSmem *gsm = reinterpret_cast<NisGroupSmem*>(sTb + 36*kuka::NB);
+    const int grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = I[i]; sTb[i] = Tbody[i]; }
     __syncthreads();
-    for (int k = blockIdx.x; k < nsamp; k += gridDim.x){
+    NisGroupSmem &s = gsm[grp];
+    kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
+    for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
+        const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;
         if (l < kuka::NX){ s.x[l] = x[k*kuka::NX + l]; } if (l < kuka::NU){ s.u[l] = u[k*kuka::NU + l]; }
         __syncwarp();
-        kuka::gradient(s.ws, s.gs, sI, sTb, s.x, s.u, s.qdd, s.dqdd);
-        for (int e = l; e < n*nm; e += 32){
-            int ky = e / n, kx = e % n;
-            float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
+        kuka::gradient<LANES>(s.ws, s.gs, sI, s.x, s.u, s.qdd, s.dqdd);
+        for (int e = l; e < n*nm; e += LANES){
+            const int ky = e / n, kx = e % n;
+            const float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
             AB[(size_t)k*n*nm + e] = FMA(dt, dxd, (ky == kx) ? 1.f : 0.f);
         }
         if (l < np){ qdd[k*np + l] = s.qdd[l]; }

@@ -114,11 +114,11 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     // dynamic shared memory of each kernel
     h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
     h->smem_sweep = ((size_t)(N-1)*n*n + (size_t)(N-1)*n + (size_t)2*N*n)*sizeof(float);
-    h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*sizeof(SimWarpSmem);
+    h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
-    h->smem_nis = 2*36*kuka::NB*sizeof(float) + NIS_WARPS*sizeof(NisWarpSmem);
-    h->smem_udyn = 2*36*kuka::NB*sizeof(float) + sizeof(SimWarpSmem);
-    h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + sizeof(NisWarpSmem);
+    h->smem_nis = 2*36*kuka::NB*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
+    h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
+    h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
     if (h->smem_sweep > 227*1024){ h->err = "N too large for the single-pass sweep staging"; return bail(PDDP_E_INVALID); }
     CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
     CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
@@ -169,7 +169,7 @@ static int launch_reset(pddp_handle h, int ignore_first){
 }
 static int launch_init(pddp_handle h){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
     DevState &S = h->S;
-    nis_kernel<<<(S.B*S.N + NIS_WARPS - 1)/NIS_WARPS, 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1);
+    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1);
     init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S);
     select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1);
     h->launches += 3;
@@ -190,7 +190,7 @@ static int launch_sweep(pddp_handle h){
 }
 static int launch_sim(pddp_handle h){
     DevState &S = h->S;
-    sim_kernel<<<S.B*S.A, 32*S.M, h->smem_sim, h->stream>>>(S);
+    sim_kernel<<<S.B*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_select(pddp_handle h){
@@ -200,7 +200,7 @@ static int launch_select(pddp_handle h){
 }
 static int launch_nis(pddp_handle h){
     DevState &S = h->S;
-    nis_kernel<<<(S.B*S.N + NIS_WARPS - 1)/NIS_WARPS, 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 0, 0);
+    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 0, 0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 
