@@ -326,7 +326,7 @@ __global__ void sweep_kernel(DevState S, int splits){
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SIM_LANES = 16;
 struct SimGroupSmem {
-    kuka::FwdWs ws;
+    kuka::FwdWsT<false> ws;
     float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
 };
 
@@ -401,8 +401,6 @@ __global__ void sim_kernel(DevState S){
             s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
         }
         __syncwarp();
-        // running cost of knot k (one lane per trajectory)
-        if (l == LANES-1 && live){ gc[k] = cost_knot(s.x, s.u, sxg, false, S); }
         kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd);
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
@@ -415,10 +413,14 @@ __global__ void sim_kernel(DevState S){
         }
         __syncwarp();
     }
-    // final-knot cost belongs to the last interval; u[N-1] is never simulated and stays the accepted one
-    if (w == S.M - 1 && live){
-        if (l == LANES-1){ gc[N-1] = cost_knot(s.x, s.u, sxg, true, S); }
-        if (l < m){ gu[(N-1)*m + l] = gup[(N-1)*m + l]; }
+    // u[N-1] is never simulated and stays the accepted one
+    if (w == S.M - 1 && live && l < m){ gu[(N-1)*m + l] = gup[(N-1)*m + l]; }
+    __syncwarp();
+    // per-knot costs of this interval, one knot per lane (the trajectory was just written by this group; the final knot
+    // belongs to the last interval)
+    if (live){
+        const int kEnd = (w == S.M - 1) ? N : kStart + NBF;
+        for (int k = kStart + l; k < kEnd; k += LANES){ gc[k] = cost_knot(gx + k*n, gu + k*m, sxg, k == N - 1, S); }
     }
 }
 
