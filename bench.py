@@ -155,8 +155,10 @@ def main():
     B, N, L1 = BATCH_PER_GPU, N_KNOTS, MAX_ITER + 1
     cfg = pddp.default_config_kuka(N, B, device=local_rank, tol_cost=0.0)
     solver = pddp.Solver(cfg)
-    # this rank's shard of the global batch: problems rank*B .. rank*B+B-1 (seed = problem index)
-    x0, u0, xg = pddp.make_inputs_kuka(N, B, seed0=rank * B)
+    # this rank's shard of the global batch (seed = problem index): problems lo .. hi-1
+    sharding = importlib.import_module("parallel-ddp_b200.sharding")
+    lo, hi = sharding.shard_range(rank, world, B * world)
+    x0, u0, xg = pddp.make_inputs_kuka(N, hi - lo, seed0=lo)
     dev = torch.device("cuda", local_rank)
     d_x0 = torch.from_numpy(x0).to(dev); d_u0 = torch.from_numpy(u0).to(dev); d_xg = torch.from_numpy(xg).to(dev)
     d_x = torch.empty_like(d_x0); d_u = torch.empty_like(d_u0)
@@ -205,7 +207,8 @@ def main():
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s, bp_ms = mx[0].item(), mx[1].item(), mx[4].item()
         iters_all, e2e_iters_all = sm[2].item(), sm[3].item()
-        its = [torch.empty_like(d_it) for _ in range(world)]; dist.all_gather(its, d_it)      # result hand-off (iteration counters) over NVLink
+        all_iters = sharding.gather_counters(d_it)      # result hand-off (per-problem iteration counters) over NCCL / NVLink
+        assert all_iters.numel() == B * world
     else:
         iters_all, e2e_iters_all, bp_ms = float(iters_rank), float(e2e_iters), phase[3]
     if rank == 0:
