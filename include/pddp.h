@@ -102,6 +102,12 @@ int pddp_phase_next_iteration(pddp_handle h);     /* nextIterationSetupGPU nisIn
 /* device time (ms) of the last phase call and the kernels it launched */
 int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
 
+/* Number of independent problem groups, each iterated on its own CUDA stream so that one group's latency-bound kernels
+ * (backward pass, sweep, selection) overlap another group's throughput-bound ones (sim, next-iteration setup).  Results do
+ * not depend on it.  Default 2 (env PDDP_GROUPS); the per-phase entries of times_ms are only filled with 1 group.
+ * Returns the value in effect. */
+int pddp_set_groups(pddp_handle h, int groups);
+
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);
 

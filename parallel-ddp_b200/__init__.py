@@ -39,7 +39,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -72,6 +72,7 @@ def load_library():
         getattr(L, f).argtypes = [H]
     L.pddp_last_phase_stats.argtypes = [H, DP, IP]
     L.pddp_last_launch_count.argtypes = [H]; L.pddp_last_launch_count.restype = C.c_long
+    L.pddp_set_groups.argtypes = [H, C.c_int]
     _lib = L
     return L
 
@@ -149,6 +150,10 @@ class Solver:
         rc = self.L.pddp_solve_device(self.h, d_x0, d_u0, d_xg, ignoreFirstDefectFlag, d_x, d_u, d_J, d_a, d_it,
                                       times.ctypes.data_as(DP) if times is not None else None)
         self._ck(rc, "pddp_solve_device")
+
+    def set_groups(self, groups):
+        """Problem groups iterated on separate streams (overlap of latency- and throughput-bound kernels); returns the value in effect."""
+        return int(self.L.pddp_set_groups(self.h, groups))
 
     def launch_count(self):
         return int(self.L.pddp_last_launch_count(self.h))

@@ -90,12 +90,12 @@ __device__ __forceinline__ void bp_prefetch(BpSmem<n,m> &s, int buf, const float
 }
 
 template <int n, int m>
-__global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur){
+__global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur, int b0){
     constexpr int nm = n + m, oHXU = n*nm, oHUU = n*nm + n, oGU = n, oB = n*n;
     static_assert(nm*nm + nm + n <= BP_THREADS && n*nm + n <= BP_THREADS, "one element per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BpSmem<n,m> &s = *reinterpret_cast<BpSmem<n,m>*>(smem_raw);
-    const int b = blockIdx.x / S.M, block = blockIdx.x % S.M, t = threadIdx.x;
+    const int b = b0 + blockIdx.x / S.M, block = blockIdx.x % S.M, t = threadIdx.x;
     if (S.done[b]){ return; }
     const int N = S.N, NBB = N / S.M;
     const float rho = S.rho[b];
@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur){
 // grid = B*splits CTAs of 32*A/splits threads; the whole (A-BK) sequence of the problem is staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------------------
 template <int n>
-__global__ void sweep_kernel(DevState S, int splits){
+__global__ void sweep_kernel(DevState S, int splits, int b0){
     extern __shared__ __align__(16) float sw[];
     // `splits` CTAs share one problem (each takes A/splits step sizes) so that a small batch still covers the SMs
-    const int b = blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
+    const int b = b0 + blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
     if (S.done[b]){ return; }
     float *sA = sw;                         // [N-1][n*n]
     float *sB = sA + (size_t)(N-1)*n*n;     // [N-1][n]
@@ -342,7 +342,7 @@ __device__ __forceinline__ float cost_knot(const float *x, const float *u, const
     return MUL(0.5f, cost);
 }
 
-__global__ void sim_kernel(DevState S){
+__global__ void sim_kernel(DevState S, int b0){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES, GPW = 32 / SIM_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw);            // 252
@@ -350,7 +350,7 @@ __global__ void sim_kernel(DevState S){
     float *sxg = sTb + 36*kuka::NB;                            // 16
     SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sxg + 16);
     const int apb = (S.A + GPW - 1) / GPW;                     // CTAs per problem
-    const int b = blockIdx.x / apb;
+    const int b = b0 + blockIdx.x / apb;
     if (S.done[b]){ return; }
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
     if (threadIdx.x < n){ sxg[threadIdx.x] = S.xGoal[b*n + threadIdx.x]; }
@@ -436,9 +436,9 @@ __global__ void init_cost_kernel(DevState S){
 // selection: J[a] (reduceSum tree order), dT[a], line search, accept/reject, rho schedule.  grid = B CTAs, one warp per alpha.
 // mode 0: iteration;  mode 1: initialisation (prevJ, Jout[0], alphaOut[0])
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void select_kernel(DevState S, int mode){
+__global__ void select_kernel(DevState S, int mode, int b0){
     extern __shared__ __align__(16) float ssel[];          // [A][N] costs + [A] J + [A] dT
-    const int b = blockIdx.x, N = S.N, A = S.A, n = S.n;
+    const int b = b0 + blockIdx.x, N = S.N, A = S.A, n = S.n;
     if (S.done[b]){ return; }
     const int a = threadIdx.x >> 5, l = threadIdx.x & 31;
     float *sJ = ssel + (size_t)A*N, *sdT = sJ + A;
@@ -515,17 +515,17 @@ struct NisGroupSmem {
 };
 constexpr int NIS_WARPS = 1;
 
-__global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode, int write_H){
+__global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode, int write_H, int b0, int nb){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, nm = n + m, np = kuka::NB, LANES = NIS_LANES, GPW = 32 / NIS_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
     NisGroupSmem *gsm = reinterpret_cast<NisGroupSmem*>(sTb + 36*kuka::NB);
     const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     const int gk = (blockIdx.x*NIS_WARPS + w)*GPW + grp, N = S.N;        // N is even: the groups of one warp share the problem
-    const int b = gk / N, k = gk % N;
+    const int b = b0 + gk / N, k = gk % N;
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
     __syncthreads();
-    if (b >= S.B || S.done[b]){ return; }
+    if (b >= b0 + nb || S.done[b]){ return; }
     NisGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;

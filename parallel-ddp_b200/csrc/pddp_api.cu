@@ -20,7 +20,10 @@ static thread_local std::string g_create_error;
 struct pddp_solver {
     pddp_config cfg;
     DevState S;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // stream 0: setup, hand-over of results, and problem group 0
+    std::vector<cudaStream_t> gstreams;     // one stream per problem group (gstreams[0] == stream)
+    std::vector<cudaEvent_t> gev;           // per-group events (fork / join)
+    int groups = 1;
     std::vector<void*> allocs;
     std::string err;
     int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
@@ -78,6 +81,10 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sms > 0){ h->num_sms = sms; } }
     CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto &e : h->ev){ CKC(cudaEventCreate(&e)); }
+    h->gstreams.push_back(h->stream);
+    for (int g = 1; g < 8; g++){ cudaStream_t st; CKC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); h->gstreams.push_back(st); }
+    for (int g = 0; g < 9; g++){ cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->gev.push_back(e); }
+    { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 2; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S));
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m, nm = n + m;
     S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter;
@@ -139,7 +146,8 @@ extern "C" void pddp_destroy(pddp_handle h){
     for (void *p : h->allocs){ cudaFree(p); }
     if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
     for (auto &e : h->ev){ cudaEventDestroy(e); }
-    cudaStreamDestroy(h->stream);
+    for (auto &e : h->gev){ cudaEventDestroy(e); }
+    for (auto st : h->gstreams){ cudaStreamDestroy(st); }
     delete h;
 }
 
@@ -169,65 +177,77 @@ static int launch_reset(pddp_handle h, int ignore_first){
 }
 static int launch_init(pddp_handle h){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
     DevState &S = h->S;
-    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1);
+    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1, 0, S.B);
     init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S);
-    select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1);
+    select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1, 0);
     h->launches += 3;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_bp(pddp_handle h){
-    DevState &S = h->S; h->cur ^= 1;
-    bp_kernel<kuka::NX, kuka::NU><<<S.B*S.M, BP_THREADS, h->smem_bp, h->stream>>>(S, h->cur);
+// problems [b0, b0+nb) on stream st
+static int launch_bp(pddp_handle h, cudaStream_t st, int b0, int nb){
+    DevState &S = h->S;
+    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_THREADS, h->smem_bp, st>>>(S, h->cur, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
-static int launch_sweep(pddp_handle h){
+static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S; if (S.M == 1){ return 0; }
     // enough CTAs to cover the SMs: split the step sizes of one problem over up to A CTAs (power-of-two divisor of A)
-    int splits = 1; while (S.B*splits*2 <= h->num_sms && (S.A % (splits*2)) == 0){ splits *= 2; }
-    sweep_kernel<kuka::NX><<<S.B*splits, 32*(S.A/splits), h->smem_sweep, h->stream>>>(S, splits);
+    int splits = 1; while (nb*splits*2 <= h->num_sms && (S.A % (splits*2)) == 0){ splits *= 2; }
+    sweep_kernel<kuka::NX><<<nb*splits, 32*(S.A/splits), h->smem_sweep, st>>>(S, splits, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
-static int launch_sim(pddp_handle h){
+static int launch_sim(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    sim_kernel<<<S.B*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S);
+    sim_kernel<<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
-static int launch_select(pddp_handle h){
+static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 0);
+    select_kernel<<<nb, 32*S.A, h->smem_sel, st>>>(S, 0, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
-static int launch_nis(pddp_handle h){
+static int launch_nis(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 0, 0);
+    nis_kernel<<<(nb*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, st>>>(S, 0, 0, b0, nb);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 
-// the iteration loop of runiLQR_GPU (DDPWrappers.cuh:52-114) with all host decisions moved to select_kernel
-static int run_iterations(pddp_handle h, double *times_ms){
+// the iteration loop of runiLQR_GPU (DDPWrappers.cuh:52-114) with all host decisions moved to select_kernel.
+// The batch is cut into `groups` problem groups, each on its own stream: problems are independent, so the latency-bound
+// kernels of one group (backward pass, sweep, selection) run under the throughput-bound ones (sim, nis) of another.
+static int run_iterations(pddp_handle h, double *times_ms, int groups){
     DevState &S = h->S;
-    const bool timing = times_ms != nullptr;
+    const bool timing = times_ms != nullptr && groups == 1;
     std::vector<cudaEvent_t> evs;
     auto mark = [&](){ if (timing){ cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); } };
     const bool poll = h->cfg.tol_cost > 0.0f;
+    // fork: every group stream starts after the setup on stream 0
+    if (groups > 1){ CK(cudaEventRecord(h->gev[8], h->stream)); for (int g = 1; g < groups; g++){ CK(cudaStreamWaitEvent(h->gstreams[g], h->gev[8], 0)); } }
     int it_done = 0;
     for (int it = 0; it < S.max_iter; it++){
-        int rc;
-        mark(); if ((rc = launch_bp(h))){ return rc; }
-        mark(); if ((rc = launch_sweep(h))){ return rc; }
-        mark(); if ((rc = launch_sim(h))){ return rc; }
-        mark(); if ((rc = launch_select(h))){ return rc; }
-        mark(); if ((rc = launch_nis(h))){ return rc; }
+        h->cur ^= 1;
+        for (int g = 0; g < groups; g++){
+            const int b0 = (int)((long)S.B*g/groups), nb = (int)((long)S.B*(g+1)/groups) - b0; cudaStream_t st = h->gstreams[g]; int rc;
+            mark(); if ((rc = launch_bp(h, st, b0, nb))){ return rc; }
+            mark(); if ((rc = launch_sweep(h, st, b0, nb))){ return rc; }
+            mark(); if ((rc = launch_sim(h, st, b0, nb))){ return rc; }
+            mark(); if ((rc = launch_select(h, st, b0, nb))){ return rc; }
+            mark(); if ((rc = launch_nis(h, st, b0, nb))){ return rc; }
+        }
         it_done = it + 1;
         if (poll && (it % 4) == 3){
-            // convergence-driven early exit: look at the active-problem counter without draining the pipeline more than needed
+            // convergence-driven early exit: read the active-problem counter once all groups reached this iteration
+            for (int g = 1; g < groups; g++){ CK(cudaStreamSynchronize(h->gstreams[g])); }
             CK(cudaMemcpyAsync(h->h_nactive, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             if (*h->h_nactive == 0){ break; }
         }
     }
     mark();
+    // join: stream 0 continues after every group
+    for (int g = 1; g < groups; g++){ CK(cudaEventRecord(h->gev[g], h->gstreams[g])); CK(cudaStreamWaitEvent(h->stream, h->gev[g], 0)); }
+    if (times_ms){ times_ms[1] = times_ms[2] = times_ms[3] = times_ms[4] = 0.0; }
     if (timing){
         CK(cudaStreamSynchronize(h->stream));
         double acc[5] = {0,0,0,0,0};
@@ -252,7 +272,7 @@ extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *
     CK(cudaMemcpyAsync(S.xGoal, d_xGoal, (size_t)B*n*4, cudaMemcpyDeviceToDevice, h->stream));
     if ((rc = launch_init(h))){ return rc; }
     CK(cudaEventRecord(h->ev[1], h->stream));
-    if ((rc = run_iterations(h, times_ms))){ return rc; }
+    if ((rc = run_iterations(h, times_ms, h->groups))){ return rc; }
     CK(cudaEventRecord(h->ev[2], h->stream));
     store_kernel<<<B, 256, 0, h->stream>>>(S, d_x_out ? d_x_out : h->d_xout, d_u_out ? d_u_out : h->d_uout, d_iters_out ? d_iters_out : h->d_iters);
     h->launches += 1; CK(cudaGetLastError());
@@ -297,6 +317,10 @@ extern "C" int pddp_solve(pddp_handle h, const float *x0, const float *u0, const
 }
 
 extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
+extern "C" int pddp_set_groups(pddp_handle h, int groups){
+    if (!h || groups < 1 || groups > 8){ return PDDP_E_INVALID; }
+    h->groups = (h->S.B >= 2*groups || groups == 1) ? groups : 1; return h->groups;
+}
 
 // WAFR_iLQR_examples.cu:67-121 with one std::default_random_engine(seed) per problem (the deterministic harness' inputs)
 extern "C" int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal){
@@ -391,11 +415,11 @@ extern "C" int pddp_phase_load_init(pddp_handle h, const float *x0, const float 
         return launch_init(h);
     });
 }
-extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_bp(h); }); }
-extern "C" int pddp_phase_forward_sweep(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sweep(h); }); }
-extern "C" int pddp_phase_forward_sim(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sim(h); }); }
-extern "C" int pddp_phase_line_search(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_select(h); }); }
-extern "C" int pddp_phase_next_iteration(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_nis(h); }); }
+extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ h->cur ^= 1; return launch_bp(h, h->stream, 0, h->S.B); }); }
+extern "C" int pddp_phase_forward_sweep(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sweep(h, h->stream, 0, h->S.B); }); }
+extern "C" int pddp_phase_forward_sim(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sim(h, h->stream, 0, h->S.B); }); }
+extern "C" int pddp_phase_line_search(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_select(h, h->stream, 0, h->S.B); }); }
+extern "C" int pddp_phase_next_iteration(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_nis(h, h->stream, 0, h->S.B); }); }
 extern "C" int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches){
     if (!h){ return PDDP_E_INVALID; } if (ms){ *ms = h->last_ms; } if (launches){ *launches = h->last_launches; } return 0;
 }
