@@ -121,7 +121,7 @@ class Solver:
                            du=((B, N, m), f), ApBK=((B, N, n, n), f), Bdu=((B, N, n), f), xGoal=((B, n), f), costk=((B, A, N), f),
                            J=((B, A), f), dT=((B, A), f), dJexp=((B, 2 * M), f), rho=((B,), f), drho=((B,), f), prevJ=((B,), f),
                            dJ=((B,), f), z=((B,), f), iter=((B,), i), alphaIndex=((B,), i), ignore_defect=((B,), i), done=((B,), i),
-                           accepted=((B,), i), final_src=((B,), i), Jout=((B, cfg.max_iter + 1), f), alphaOut=((B, cfg.max_iter + 1), i))
+                           accepted=((B,), i), final_src=((B,), i), dbg=((4096,), np.int64), Jout=((B, cfg.max_iter + 1), f), alphaOut=((B, cfg.max_iter + 1), i))
 
     def _ck(self, rc, what):
         if rc != 0:

@@ -19,6 +19,10 @@
 
 namespace pddp {
 
+// Knot strides (floats) of AB, H and g in HBM: the 14x21 / 21x21 / 21 tiles padded to 16-byte multiples so that one
+// cp.async.bulk (TMA) moves a whole tile; the tile interior keeps the reference's column-major layout.
+constexpr int AB_STRIDE = 296, H_STRIDE = 444, G_STRIDE = 24;
+
 struct DevState {
     // sizes
     int B, N, A, M, n, m, max_iter;
@@ -41,6 +45,7 @@ struct DevState {
     int *iter, *alphaIndex, *ignore_defect, *done, *accepted, *final_src;
     float *Jout; int *alphaOut;    // [B][max_iter+1]
     int *n_active;                 // [1]
+    long long *dbg;                // [4096] stage clocks of CTA 0 (only written by -DPDDP_BP_TRACE builds)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -54,220 +59,239 @@ __device__ __forceinline__ void cp_async_commit(){ asm volatile("cp.async.commit
 template <int N_> __device__ __forceinline__ void cp_async_wait(){ asm volatile("cp.async.wait_group %0;\n" :: "n"(N_)); }
 
 // ------------------------------------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p){ return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count){ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes){
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar){
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity){
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // backward pass
 // ------------------------------------------------------------------------------------------------------------------
 // One CTA of BP_THREADS (16 warps) per (problem, time block).  Every knot is five barrier-separated stages; inside a
-// stage each thread owns at most one output element (a 14- or 7-term fused chain), its indices fixed before the knot
-// loop.  The 7x7 Huu inverse is the serial bottleneck of a knot, so warp 0 computes Huu first and eliminates it in
-// registers (shuffles) while warps 1..15 assemble the other 392 entries of H and g.  The inputs of knot k-1 (AB, H, g,
-// d: 3.1 KB) are in flight (LDGSTS) while knot k is processed.
-constexpr int BP_THREADS = 512;
+// stage each thread owns at most one output element (a 14- or 7-term fused chain, operands pre-loaded into registers so
+// that all shared-memory loads of the chain are in flight together), its indices fixed before the knot loop.  The 7x7
+// Huu inverse is the serial bottleneck of a knot, so warp 0 computes Huu first and eliminates it in registers (shuffles)
+// while warps 1..15 assemble the other 392 entries of H and g.  The per-knot inputs (AB, H, g: 3 KB) stream through a
+// BP_STAGES-deep ring in shared memory filled by TMA bulk copies (cp.async.bulk + mbarrier), issued by one thread
+// BP_STAGES-1 knots ahead of their use.
+constexpr int BP_THREADS = 256;
+constexpr int BP_STAGES = 4;
 template <int n, int m>
-struct BpSmem {
+struct __align__(16) BpSmem {
     static constexpr int nm = n + m;
-    float AB[2][n*nm];      // double-buffered inputs of the knot being processed / prefetched
-    float Hc[2][nm*nm];
-    float gc[2][nm];
-    float dk[2][n];
-    float P[n*n], p[n];
-    float AB2[n*nm];        // AB'(P+rho) then K'Huu - Hxu
-    float H[nm*nm], g[nm];
-    float K[m*n], du[m];
+    float AB[BP_STAGES][AB_STRIDE];      // ring of knot inputs
+    float Hc[BP_STAGES][H_STRIDE];
+    float gc[BP_STAGES][G_STRIDE];
+    unsigned long long full[BP_STAGES];
+    float P[n*n], p[n + 2];
+    float Pr[n*n];          // P + rho on the diagonal: the (P + rho I) operand of the u-rows of AB'(.) (bpHelpers.cuh:62)
+    float AB2[n*nm];        // AB'(P+rho), later K'Huu - Hxu
+    float H[nm*nm + 3], g[nm + 3];
+    float K[m*n], du[m + 1];
     float Huu[2*m*m];
-    float dx[n];
-    float dJ[2*m];
+    float dx[n + 2];
+    float dJ[2*m + 2];
 };
 
-template <int n, int m>
-__device__ __forceinline__ void bp_prefetch(BpSmem<n,m> &s, int buf, const float *gAB, const float *gH, const float *gg, const float *gd){
-    constexpr int nm = n + m;
-    const int t = threadIdx.x;
-    if (t < n*nm){ cp_async4(&s.AB[buf][t], gAB + t); }
-    if (t < nm*nm){ cp_async4(&s.Hc[buf][t], gH + t); }
-    if (t >= nm*nm && t < nm*nm + nm){ cp_async4(&s.gc[buf][t - nm*nm], gg + t - nm*nm); }
-    if (t >= nm*nm + nm && t < nm*nm + nm + n){ cp_async4(&s.dk[buf][t - nm*nm - nm], gd + t - nm*nm - nm); }
-    cp_async_commit();
+// keeps the operand loads of a chain ahead of its first FMA (all LDS in flight together)
+#define SCHED_FENCE() asm volatile("" ::: "memory")
+#ifdef PDDP_BP_TRACE
+#define BP_TRACE(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && iter >= iterCount - 7){ S.dbg[(iterCount - iter)*8 + (slot)] = clock64(); } } while (0)
+#else
+#define BP_TRACE(slot) do { } while (0)
+#endif
+
+// K-term fused chain val = sum_j a[j*sa] * b[j*sb], j ascending, operands loaded first
+template <int K>
+__device__ __forceinline__ float chain(const float *a, int sa, const float *b, int sb){
+    float x[K], y[K];
+    #pragma unroll
+    for (int j = 0; j < K; j++){ x[j] = a[j*sa]; y[j] = b[j*sb]; }
+    float val = 0.f;
+    #pragma unroll
+    for (int j = 0; j < K; j++){ val = FMA(x[j], y[j], val); }
+    return val;
 }
 
 template <int n, int m>
-__global__ void __launch_bounds__(BP_THREADS) bp_kernel(DevState S, int cur, int b0){
-    constexpr int nm = n + m, oHXU = n*nm, oHUU = n*nm + n, oGU = n, oB = n*n;
-    static_assert(nm*nm + nm + n <= BP_THREADS && n*nm + n <= BP_THREADS, "one element per thread");
+__global__ void __launch_bounds__(BP_THREADS, 2) bp_kernel(DevState S, int cur, int b0){
+    constexpr int nm = n + m, oHXU = n*nm, oHUU = n*nm + n, oGU = n, oB = n*n, T_ = BP_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BpSmem<n,m> &s = *reinterpret_cast<BpSmem<n,m>*>(smem_raw);
     const int b = b0 + blockIdx.x / S.M, block = blockIdx.x % S.M, t = threadIdx.x;
     if (S.done[b]){ return; }
     const int N = S.N, NBB = N / S.M;
     const float rho = S.rho[b];
-    float *gP = S.Pbuf[cur] + (size_t)b*N*n*n, *gp = S.pbuf[cur] + (size_t)b*N*n;
-    const float *gPp = S.Pbuf[cur^1] + (size_t)b*N*n*n, *gpp = S.pbuf[cur^1] + (size_t)b*N*n;
-    const float *gAB = S.AB + (size_t)b*N*n*nm, *gH = S.H + (size_t)b*N*nm*nm, *gg = S.g + (size_t)b*N*nm;
-    const float *gd = S.dp + (size_t)b*N*n, *gx = S.xp + (size_t)b*N*n, *gx2 = S.xp2 + (size_t)b*N*n;
-    float *gKT = S.KT + (size_t)b*N*n*m, *gdu = S.du + (size_t)b*N*m, *gApBK = S.ApBK + (size_t)b*N*n*n, *gBdu = S.Bdu + (size_t)b*N*n;
-
-    // ---- per-thread roles, fixed for the whole block of knots
-    // stage A: element t of AB2 (t < n*nm); threads n*nm .. n*nm+n-1 update p
-    const int a_ky = t / nm, a_kx = t % nm;
-    // stage B: warp 0 -> Huu (2 per lane) then the elimination; threads 32.. -> the other H entries, then g
-    int b_kx = -1, b_ky = 0;
-    {
-        const int item = t - 32;
-        if (item >= 0 && item < n*nm){ b_ky = item / nm; b_kx = item % nm; }                               // columns 0..n-1, all rows
-        else if (item >= n*nm && item < n*nm + m*n){ const int q = item - n*nm; b_ky = n + q / n; b_kx = q % n; } // columns n.., rows 0..n-1
-    }
-    const int b_g = (t - 32 - (nm*nm - m*m));          // 0..nm-1 -> g
-    // stage C: K element t (t < n*m): kx = row of K (m), ky = column (n); threads 128.. -> du
-    const int c_ky = t / m, c_kx = t % m;
-    // stage D: [0, n*m) T;  [128, 128+n*n) ApBK;  [352, 352+n) Bdu;  [384, 384+m) expected reduction;  [400, 400+n*m) KT store; [500,500+m) du store
-    const int d_ky = t / n, d_kx = t % n;                       // T (ky < m) and KT store
-    const int d2 = t - 128, d2_ky = d2 / n, d2_kx = d2 % n;     // ApBK
-    // stage E: P element t (t < n*n); threads 256.. -> p
-    const int e_ky = t / n, e_kx = t % n;
+    const size_t bN = (size_t)b*N;
 
     int ks = NBB*(block+1) - 1, iterCount;
-    float dJ0 = 0.f, dJ1 = 0.f;          // thread 384+ind: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
-    if (ks == N - 1){
+    const bool last_block = (ks == N - 1);
+    if (last_block){ ks--; iterCount = NBB - 2; } else { iterCount = NBB - 1; }
+    const int nknots = iterCount + 1, ks0 = ks;                   // knots ks0, ks0-1, ... ks0-nknots+1
+    // ---- ring setup + first BP_STAGES-1 loads
+    if (t == 0){
+        for (int q = 0; q < BP_STAGES; q++){ mbar_init(&s.full[q], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int i){       // load knot number i (processing order) into slot i % BP_STAGES; thread 0 only
+        const int slot = i % BP_STAGES; const size_t k = bN + ks0 - i;
+        mbar_expect_tx(&s.full[slot], (AB_STRIDE + H_STRIDE + G_STRIDE)*4);
+        tma_load_1d(s.AB[slot], S.AB + k*AB_STRIDE, AB_STRIDE*4, &s.full[slot]);
+        tma_load_1d(s.Hc[slot], S.H + k*H_STRIDE, H_STRIDE*4, &s.full[slot]);
+        tma_load_1d(s.gc[slot], S.g + k*G_STRIDE, G_STRIDE*4, &s.full[slot]);
+    };
+    if (t == 0){ for (int i = 0; i < BP_STAGES-1 && i < nknots; i++){ issue(i); } }
+
+    float dJ0 = 0.f, dJ1 = 0.f;          // threads 52..58: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
+    if (last_block){
         // final block: Hxx[N-1] -> P[N-2], gx[N-1] -> p[N-2]  (bpHelpers.cuh:362-367)
-        if (t < n*n){ const int kx = t % n, ky = t / n; float v = MUL(1.0f, gH[(size_t)ks*nm*nm + kx + nm*ky]); s.P[t] = v; gP[(size_t)(ks-1)*n*n + t] = v; }
-        if (t >= 256 && t < 256 + n){ const int r = t - 256; float v = MUL(1.0f, gg[ks*nm + r]); s.p[r] = v; gp[(ks-1)*n + r] = v; }
-        ks--; iterCount = NBB - 2;
-        __syncthreads();
+        const size_t kN = bN + N - 1; float *gP = S.Pbuf[cur] + (kN-1)*n*n, *gp = S.pbuf[cur] + (kN-1)*n;
+        if (t < n*n){ const int kx = t % n, ky = t / n; const float v = MUL(1.0f, S.H[kN*H_STRIDE + kx + nm*ky]); s.P[t] = v; s.Pr[t] = (kx == ky) ? ADD(v, rho) : v; gP[t] = v; }
+        if (t >= 224 && t < 224 + n){ const int r = t - 224; const float v = MUL(1.0f, S.g[kN*G_STRIDE + r]); s.p[r] = v; gp[r] = v; }
     } else {
         // other blocks: start from the previous iteration's P,p at the block boundary, shifted to the new linearisation point
-        iterCount = NBB - 1;
-        if (t < n*n){ s.P[t] = gPp[(size_t)ks*n*n + t]; }
-        if (t >= 256 && t < 256 + n){ const int r = t - 256; s.dx[r] = SUB(gx[(ks+1)*n + r], gx2[(ks+1)*n + r]); }
+        const float *gPp = S.Pbuf[cur^1] + (bN + ks)*n*n;
+        if (t < n*n){ const float v = gPp[t]; s.P[t] = v; s.Pr[t] = (t % n == t / n) ? ADD(v, rho) : v; }
+        if (t >= 224 && t < 224 + n){ const int r = t - 224; s.dx[r] = SUB(S.xp[(bN + ks + 1)*n + r], S.xp2[(bN + ks + 1)*n + r]); }
         __syncthreads();
-        if (t < n){
-            float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(s.P[t + n*j], s.dx[j], val); }
-            s.p[t] = FMA(1.0f, val, gpp[ks*n + t]);
-        }
-        __syncthreads();
+        if (t < n){ s.p[t] = FMA(1.0f, chain<n>(&s.P[t], n, s.dx, 1), S.pbuf[cur^1][(bN + ks)*n + t]); }
     }
-    bp_prefetch<n,m>(s, 0, gAB + (size_t)ks*n*nm, gH + (size_t)ks*nm*nm, gg + ks*nm, gd + ks*n);
-    int buf = 0;
+    __syncthreads();
     #pragma unroll 1
-    for (int iter = iterCount; iter >= 0; iter--, ks--, buf ^= 1){
-        if (iter > 0){ bp_prefetch<n,m>(s, buf^1, gAB + (size_t)(ks-1)*n*nm, gH + (size_t)(ks-1)*nm*nm, gg + (ks-1)*nm, gd + (ks-1)*n); cp_async_wait<1>(); }
-        else { cp_async_wait<0>(); }
-        __syncthreads();
-        const float *sAB = s.AB[buf], *bH = s.Hc[buf], *bg = s.gc[buf], *bd = s.dk[buf];
+    for (int iter = iterCount, i = 0; iter >= 0; iter--, ks--, i++){
+        const int slot = i % BP_STAGES;
+        // refill the slot freed by the previous knot (all of its readers are past the barrier that ended that knot)
+        if (t == 0 && i + BP_STAGES - 1 < nknots){ issue(i + BP_STAGES - 1); }
+        BP_TRACE(0);
+        mbar_wait(&s.full[slot], (i / BP_STAGES) & 1);
+        BP_TRACE(1);
+        const float *sAB = s.AB[slot], *bH = s.Hc[slot], *bg = s.gc[slot];
+        const size_t kk = bN + ks;
+        const bool boundary = S.M > 1 && iter == NBB - 1;      // block-local defect-boundary test of the reference (bpHelpers.cuh:73)
         // ---- stage A: AB2 = AB'(P + rho I[u rows]);  p += P d on the block-local defect boundary (bpHelpers.cuh:54-81)
-        if (t < n*nm){
-            float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(sAB[a_kx*n+j], ADD(s.P[a_ky*n+j], (a_kx >= n && a_ky == j) ? rho : 0.f), val); }
-            s.AB2[a_ky*nm+a_kx] = val;
-        } else if (t < n*nm + n){
-            const int r = t - n*nm; float val = 0.f;
-            if (S.M > 1 && (((iter+1) % NBB) == 0) && iter < N-1){
-                #pragma unroll
-                for (int j = 0; j < n; j++){ val = FMA(bd[j], ADD(s.P[r + j*n], 0.f), val); }
+        #pragma unroll
+        for (int q = 0; q < 2; q++){
+            const int e = t + T_*q;
+            if (e < n*nm){
+                // x-rows use P (the reference adds +0, an identity), u-rows use P + rho on the diagonal
+                const int ky = e / nm, kx = e % nm;
+                s.AB2[ky*nm+kx] = chain<n>(&sAB[kx*n], 1, (kx >= n ? s.Pr : s.P) + ky*n, 1);
+            } else if (e < n*nm + n){
+                const int r = e - n*nm; float val = 0.f;
+                if (boundary){ val = chain<n>(S.dp + kk*n, 1, &s.P[r], n); }
+                s.p[r] = ADD(s.p[r], val);
             }
-            s.p[r] = ADD(s.p[r], val);
         }
         __syncthreads();
-        // ---- stage B: H = (AB2 AB)' + H_cost, g = AB'p + g_cost; warp 0 does Huu first and inverts it meanwhile
+        BP_TRACE(2);
+        // ---- stage B1: first half of H = (AB2 AB)' + H_cost: threads 0..48 take the Huu block (needed first), the others
+        //      the start of the remaining 392 entries and g
+        {
+            if (t < m*m){
+                const int ky = n + t / m, kx = n + t % m;
+                const float h = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
+                s.H[kx+nm*ky] = h;
+                s.Huu[(kx-n) + m*(ky-n)] = MUL(1.0f, h); s.Huu[m*m + (ky-n)*m + (kx-n)] = (kx == ky) ? 1.f : 0.f;
+            } else {
+                const int item = t - m*m;                         // 0 .. 206
+                int kx, ky;
+                if (item < n*nm){ ky = item / nm; kx = item % nm; } else { const int r = item - n*nm; ky = n + r / n; kx = r % n; }
+                s.H[kx+nm*ky] = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
+            }
+        }
+        __syncthreads();
+        BP_TRACE(3);
+        // ---- stage B2: warp 0 inverts Huu in registers while warps 1..7 finish H and g
         if (t < 32){
-            #pragma unroll
-            for (int q = 0; q < 2; q++){
-                const int e = t + 32*q;
-                if (e < m*m){
-                    const int ky = n + e / m, kx = n + e % m; float val = 0.f;
-                    #pragma unroll
-                    for (int j = 0; j < n; j++){ val = FMA(s.AB2[ky+nm*j], sAB[kx*n+j], val); }
-                    const float h = FMA(1.0f, val, MUL(1.0f, bH[kx+nm*ky]));
-                    s.H[kx+nm*ky] = h;
-                    s.Huu[(kx-n) + m*(ky-n)] = MUL(1.0f, h); s.Huu[m*m + (ky-n)*m + (kx-n)] = (kx == ky) ? 1.f : 0.f;
-                }
-            }
-            __syncwarp();
-            gauss_jordan_warp_reg<m>(s.Huu);
+            gauss_jordan_group<m, 32>(s.Huu);
+            BP_TRACE(4);
         } else {
-            if (b_kx >= 0){
-                float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < n; j++){ val = FMA(s.AB2[b_ky+nm*j], sAB[b_kx*n+j], val); }
-                s.H[b_kx+nm*b_ky] = FMA(1.0f, val, MUL(1.0f, bH[b_kx+nm*b_ky]));
-            } else if (b_g >= 0 && b_g < nm){
-                float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < n; j++){ val = FMA(s.p[j], sAB[b_g*n+j], val); }
-                s.g[b_g] = FMA(1.0f, val, MUL(1.0f, bg[b_g]));
+            const int item = (T_ - m*m) + (t - 32);               // 207 .. 430
+            if (item < nm*nm - m*m){
+                int kx, ky;
+                if (item < n*nm){ ky = item / nm; kx = item % nm; } else { const int r = item - n*nm; ky = n + r / n; kx = r % n; }
+                s.H[kx+nm*ky] = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
+            } else if (item < nm*nm - m*m + nm){
+                const int r = item - (nm*nm - m*m);
+                s.g[r] = FMA(1.0f, chain<n>(s.p, 1, &sAB[r*n], 1), MUL(1.0f, bg[r]));
             }
         }
         __syncthreads();
+        BP_TRACE(5);
         const float *Hinv = &s.Huu[m*m];
         // ---- stage C: K = Huu^-1 Hux, du = Huu^-1 gu (bpHelpers.cuh:206-220)
         if (t < n*m){
-            float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < m; j++){ val = FMA(Hinv[c_kx+m*j], s.H[oGU + c_ky*nm + j], val); }
-            s.K[c_kx+c_ky*m] = MUL(1.0f, val);
+            const int ky = t / m, kx = t % m;
+            s.K[kx+ky*m] = MUL(1.0f, chain<m>(&Hinv[kx], m, &s.H[oGU + ky*nm], 1));
         } else if (t >= 128 && t < 128 + m){
-            const int r = t - 128; float val = 0.f;
-            #pragma unroll
-            for (int j = 0; j < m; j++){ val = FMA(Hinv[r+m*j], s.g[oGU+j], val); }
-            s.du[r] = ADD(MUL(1.0f, val), 0.f);
+            const int r = t - 128;
+            s.du[r] = ADD(MUL(1.0f, chain<m>(&Hinv[r], m, &s.g[oGU], 1)), 0.f);
         }
         __syncthreads();
+        BP_TRACE(6);
         // ---- stage D: T = K'Huu - Hxu (into AB2), A-BK, B du, expected reduction, KT/du to HBM
         const bool do_ctg = (iter != 0 || block != 0);
-        if (t < n*m){
-            if (do_ctg){
-                float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < m; j++){ val = FMA(s.K[d_kx*m+j], s.H[oHUU+d_ky*nm+j], val); }
-                s.AB2[d_kx+d_ky*n] = SUB(val, s.H[oHXU+d_kx+nm*d_ky]);
+        #pragma unroll
+        for (int q = 0; q < 2; q++){
+            const int e = t + T_*q;
+            if (e < n*m){
+                if (do_ctg){ const int ky = e / n, kx = e % n; s.AB2[kx+ky*n] = SUB(chain<m>(&s.K[kx*m], 1, &s.H[oHUU+ky*nm], 1), s.H[oHXU+kx+nm*ky]); }
+            } else if (e < n*m + n*n){
+                if (S.M > 1){ const int r = e - n*m, ky = r / n, kx = r % n; S.ApBK[kk*n*n + kx + n*ky] = SUB(sAB[kx+n*ky], chain<m>(&sAB[oB+kx], n, &s.K[ky*m], 1)); }
+            } else if (e < n*m + n*n + n){
+                if (S.M > 1){ const int kx = e - n*m - n*n; S.Bdu[kk*n + kx] = chain<m>(&sAB[oB+kx], n, s.du, 1); }
+            } else if (e < n*m + n*n + n + m){
+                const int ind = e - (n*m + n*n + n);
+                const float dot = chain<m>(&s.H[oHUU+ind], nm, s.du, 1);
+                dJ0 = FMA(s.du[ind], s.g[oGU+ind], dJ0); dJ1 = FMA(s.du[ind], dot, dJ1);
+            } else if (e < n*m + n*n + n + m + n*m){
+                const int r = e - (n*m + n*n + n + m), ky = r / n, kx = r % n;
+                S.KT[kk*n*m + kx + n*ky] = s.K[ky + m*kx];
+            } else if (e < n*m + n*n + n + m + n*m + m){
+                const int r = e - (n*m + n*n + n + m + n*m); S.du[kk*m + r] = s.du[r];
             }
-        } else if (t >= 128 && t < 128 + n*n){
-            if (S.M > 1){
-                float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < m; j++){ val = FMA(sAB[oB+d2_kx+n*j], s.K[d2_ky*m+j], val); }
-                gApBK[(size_t)ks*n*n + d2_kx + n*d2_ky] = SUB(sAB[d2_kx+n*d2_ky], val);
-            }
-        } else if (t >= 352 && t < 352 + n){
-            if (S.M > 1){
-                const int kx = t - 352; float val = 0.f;
-                #pragma unroll
-                for (int j = 0; j < m; j++){ val = FMA(sAB[oB+kx+n*j], s.du[j], val); }
-                gBdu[ks*n + kx] = val;
-            }
-        } else if (t >= 384 && t < 384 + m){
-            const int ind = t - 384; float dot = 0.f;
-            #pragma unroll
-            for (int j = 0; j < m; j++){ dot = FMA(s.H[oHUU+ind+nm*j], s.du[j], dot); }
-            dJ0 = FMA(s.du[ind], s.g[oGU+ind], dJ0); dJ1 = FMA(s.du[ind], dot, dJ1);
-        } else if (t >= 400 && t < 400 + n*m){
-            const int e = t - 400, ky = e / n, kx = e % n;
-            gKT[(size_t)ks*n*m + kx + n*ky] = s.K[ky + m*kx];
-        } else if (t >= 500 && t < 500 + m){
-            gdu[ks*m + t - 500] = s.du[t - 500];
         }
         __syncthreads();
+        BP_TRACE(7);
         // ---- stage E: cost-to-go of the previous knot (bpHelpers.cuh:223-276)
         if (do_ctg){
             if (t < n*n){
+                const int ky = t / n, kx = t % n;
+                float a[m], c[m], k2[m], h2[m];
+                #pragma unroll
+                for (int j = 0; j < m; j++){ a[j] = s.AB2[kx+n*j]; c[j] = s.K[ky*m+j]; k2[j] = s.K[kx*m+j]; h2[j] = s.H[oGU+ky*nm+j]; }
                 float val = 0.f;
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.AB2[e_kx+n*j], s.K[e_ky*m+j], -MUL(s.K[e_kx*m+j], s.H[oGU+e_ky*nm+j]))); }
-                const float v = ADD(s.H[e_kx+e_ky*nm], val);
-                s.P[t] = v; gP[(size_t)(ks-1)*n*n + t] = v;
-            } else if (t >= 256 && t < 256 + n){
-                const int r = t - 256; float val = 0.f;
+                for (int j = 0; j < m; j++){ val = ADD(val, FMA(a[j], c[j], -MUL(k2[j], h2[j]))); }
+                const float v = ADD(s.H[kx+ky*nm], val);
+                s.P[t] = v; s.Pr[t] = (kx == ky) ? ADD(v, rho) : v; S.Pbuf[cur][(kk-1)*n*n + t] = v;
+            } else if (t >= 224 && t < 224 + n){
+                const int r = t - 224; float val = 0.f;
                 #pragma unroll
                 for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], s.AB2[r+n*j], -MUL(s.K[r*m+j], s.g[oGU+j]))); }
                 const float v = ADD(s.g[r], val);
-                s.p[r] = v; gp[(ks-1)*n + r] = v;
+                s.p[r] = v; S.pbuf[cur][(kk-1)*n + r] = v;
             }
         }
-        // the next iteration's top-of-loop barrier orders stage E's writes before stage A's reads
+        __syncthreads();      // P,p of the next knot are complete; the ring slot of this knot is free
     }
     // ---- expected cost reduction of this block: thread 0 sums the m per-thread partials in order (bpHelpers.cuh:416)
-    if (t >= 384 && t < 384 + m){ s.dJ[t-384] = dJ0; s.dJ[m + t-384] = dJ1; }
+    {
+        const int e = t + T_, base = n*m + n*n + n;
+        if (e >= base && e < base + m){ s.dJ[e-base] = dJ0; s.dJ[m + e-base] = dJ1; }
+    }
     __syncthreads();
     if (t == 0){
         float a0 = s.dJ[0], a1 = s.dJ[m];
@@ -541,14 +565,14 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     __syncwarp();
     // cost gradient (plants/cost_arm.cuh:156-202)
     const float *xg = S.xGoal + b*n;
-    float *gg = S.g + ((size_t)b*N + k)*nm;
+    float *gg = S.g + ((size_t)b*N + k)*G_STRIDE;
     const bool fin = (k == N - 1);
     for (int e = l; e < nm; e += LANES){
         if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
         else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
     }
     if (write_H){
-        float *gH = S.H + ((size_t)b*N + k)*nm*nm;
+        float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
         for (int e = l; e < nm*nm; e += LANES){
             const int i = e / nm, j = e % nm; float v = 0.f;
             if (fin){ if (i < n && j < n){ v = (i != j) ? 0.f : (i < np ? S.QF1 : S.QF2); } }
@@ -560,7 +584,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     // (its group still runs the collective code so that both halves of a warp stay in lockstep, but stores nothing)
     kuka::gradient<LANES>(s.ws, s.gs, sI, s.x, s.u, s.qdd, s.dqdd);
     if (fin){ return; }
-    float *gAB = S.AB + ((size_t)b*N + k)*n*nm;
+    float *gAB = S.AB + ((size_t)b*N + k)*AB_STRIDE;
     const float dt = S.dt;
     for (int e = l; e < n*nm; e += LANES){
         const int ky = e / n, kx = e % n;

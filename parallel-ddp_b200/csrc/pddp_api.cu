@@ -104,7 +104,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.I = dI; S.Tbody = dTb; S.alpha = dal;
     DA(S.x, (size_t)B*A*N*n, "x"); DA(S.u, (size_t)B*A*N*m, "u"); DA(S.d, (size_t)B*A*N*n, "d");
     DA(S.xp, (size_t)B*N*n, "xp"); DA(S.xp2, (size_t)B*N*n, "xp2"); DA(S.up, (size_t)B*N*m, "up"); DA(S.dp, (size_t)B*N*n, "dp");
-    DA(S.AB, (size_t)B*N*n*nm, "AB"); DA(S.H, (size_t)B*N*nm*nm, "H"); DA(S.g, (size_t)B*N*nm, "g");
+    DA(S.AB, (size_t)B*N*AB_STRIDE, nullptr); DA(S.H, (size_t)B*N*H_STRIDE, nullptr); DA(S.g, (size_t)B*N*G_STRIDE, nullptr);
     DA(S.Pbuf[0], (size_t)B*N*n*n, nullptr); DA(S.Pbuf[1], (size_t)B*N*n*n, nullptr); DA(S.pbuf[0], (size_t)B*N*n, nullptr); DA(S.pbuf[1], (size_t)B*N*n, nullptr);
     DA(S.KT, (size_t)B*N*n*m, "KT"); DA(S.du, (size_t)B*N*m, "du"); DA(S.ApBK, (size_t)B*N*n*n, "ApBK"); DA(S.Bdu, (size_t)B*N*n, "Bdu");
     DA(S.xGoal, (size_t)B*n, "xGoal"); DA(S.costk, (size_t)B*A*N, "costk");
@@ -114,6 +114,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     DA(S.accepted, B, "accepted"); DA(S.final_src, B, "final_src");
     DA(S.Jout, (size_t)B*(cfg->max_iter+1), "Jout"); DA(S.alphaOut, (size_t)B*(cfg->max_iter+1), "alphaOut");
     DA(S.n_active, 1, nullptr);
+    DA(S.dbg, 4096, "dbg");
     DA(h->d_xout, (size_t)B*N*n, nullptr); DA(h->d_uout, (size_t)B*N*m, nullptr); DA(h->d_iters, B, nullptr);
     h->h_stage_bytes = ((size_t)B*N*(n+m) + (size_t)B*n + (size_t)2*B*(cfg->max_iter+1) + B)*sizeof(float);
     CKC(cudaMallocHost((void**)&h->h_stage, h->h_stage_bytes));
@@ -381,14 +382,32 @@ static bool resolve(pddp_handle h, const char *name, void **p, size_t *bytes){
     if (it == h->arrays.end()){ return false; }
     *p = it->second.first; *bytes = it->second.second; return true;
 }
+// AB, H, g live in HBM with padded knot strides (kernels.cuh): the API speaks the reference's dense layout
+static bool padded(pddp_handle h, const char *name, void **p, size_t *tile, size_t *stride){
+    std::string s(name); DevState &S = h->S;
+    if (s == "AB"){ *p = S.AB; *tile = (size_t)S.n*(S.n+S.m)*4; *stride = AB_STRIDE*4; return true; }
+    if (s == "H"){ *p = S.H; *tile = (size_t)(S.n+S.m)*(S.n+S.m)*4; *stride = H_STRIDE*4; return true; }
+    if (s == "g"){ *p = S.g; *tile = (size_t)(S.n+S.m)*4; *stride = G_STRIDE*4; return true; }
+    return false;
+}
 extern "C" int pddp_set_array(pddp_handle h, const char *name, const void *src, long nbytes){
     if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    { size_t tile, stride; const size_t rows = (size_t)h->S.B*h->S.N;
+      if (padded(h, name, &p, &tile, &stride)){
+          if ((size_t)nbytes != tile*rows){ h->err = std::string("bad array size: ") + name; return PDDP_E_INVALID; }
+          CK(cudaSetDevice(h->cfg.device)); CK(cudaStreamSynchronize(h->stream));
+          CK(cudaMemcpy2D(p, stride, src, tile, tile, rows, cudaMemcpyHostToDevice)); return 0; } }
     if (!resolve(h, name, &p, &bytes) || (size_t)nbytes != bytes){ h->err = std::string("bad array name/size: ") + name; return PDDP_E_INVALID; }
     CK(cudaSetDevice(h->cfg.device)); CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice)); return 0;
 }
 extern "C" int pddp_get_array(pddp_handle h, const char *name, void *dst, long nbytes){
     if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    { size_t tile, stride; const size_t rows = (size_t)h->S.B*h->S.N;
+      if (padded(h, name, &p, &tile, &stride)){
+          if ((size_t)nbytes != tile*rows){ h->err = std::string("bad array size: ") + name; return PDDP_E_INVALID; }
+          CK(cudaSetDevice(h->cfg.device)); for (auto st : h->gstreams){ CK(cudaStreamSynchronize(st)); }
+          CK(cudaMemcpy2D(dst, tile, p, stride, tile, rows, cudaMemcpyDeviceToHost)); return 0; } }
     if (!resolve(h, name, &p, &bytes) || (size_t)nbytes != bytes){ h->err = std::string("bad array name/size: ") + name; return PDDP_E_INVALID; }
     CK(cudaSetDevice(h->cfg.device)); CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost)); return 0;
