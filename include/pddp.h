@@ -111,6 +111,10 @@ int pddp_set_groups(pddp_handle h, int groups);
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);
 
+/* self-test: compares the library's reciprocal (pddp_math.cuh rcp_rn) with the IEEE division 1.0f/x the reference
+ * compiles to (e.g. DDPHelpers/invHelpers.cuh pivot reciprocals) on all 2^32 float bit patterns; *mismatches = count. */
+int pddp_selftest_rcp(unsigned long long *mismatches);
+
 #ifdef __cplusplus
 }
 #endif

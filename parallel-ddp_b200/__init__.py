@@ -39,7 +39,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -73,6 +73,7 @@ def load_library():
     L.pddp_last_phase_stats.argtypes = [H, DP, IP]
     L.pddp_last_launch_count.argtypes = [H]; L.pddp_last_launch_count.restype = C.c_long
     L.pddp_set_groups.argtypes = [H, C.c_int]
+    L.pddp_selftest_rcp.argtypes = [C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 
@@ -97,6 +98,15 @@ def make_inputs_kuka(N, batch, seed0=0):
     x0 = np.zeros((batch, N, 14), np.float32); u0 = np.zeros((batch, N, 7), np.float32); xg = np.zeros((batch, 14), np.float32)
     L.pddp_make_inputs_kuka(N, batch, seed0, x0.ctypes.data_as(FP), u0.ctypes.data_as(FP), xg.ctypes.data_as(FP))
     return x0, u0, xg
+
+
+def selftest_rcp():
+    """Number of float bit patterns on which the library's reciprocal differs from IEEE 1.0f/x (must be 0)."""
+    L = load_library(); bad = C.c_ulonglong(0)
+    rc = L.pddp_selftest_rcp(C.byref(bad))
+    if rc != 0:
+        raise PddpError(f"pddp_selftest_rcp failed ({rc})")
+    return int(bad.value)
 
 
 class Solver:

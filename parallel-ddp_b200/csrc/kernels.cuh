@@ -75,17 +75,38 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                  :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// polling wait with back-off for the producer warp: a tight try_wait loop would keep its scheduler's shared-memory queue busy
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long *bar, unsigned parity){
+    unsigned ok = 0;
+    while (true){
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok){ break; }
+        __nanosleep(400);
+    }
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar){ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+// named barrier over the first `count` threads' warps (the producer warp of a CTA does not take part)
+__device__ __forceinline__ void bar_sync(int id, int count){ asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(count) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------------
 // backward pass
 // ------------------------------------------------------------------------------------------------------------------
-// One CTA of BP_THREADS (16 warps) per (problem, time block).  Every knot is five barrier-separated stages; inside a
-// stage each thread owns at most one output element (a 14- or 7-term fused chain, operands pre-loaded into registers so
-// that all shared-memory loads of the chain are in flight together), its indices fixed before the knot loop.  The 7x7
-// Huu inverse is the serial bottleneck of a knot, so warp 0 computes Huu first and eliminates it in registers (shuffles)
-// while warps 1..15 assemble the other 392 entries of H and g.  The per-knot inputs (AB, H, g: 3 KB) stream through a
-// BP_STAGES-deep ring in shared memory filled by TMA bulk copies (cp.async.bulk + mbarrier), issued by one thread
-// BP_STAGES-1 knots ahead of their use.
-constexpr int BP_THREADS = 256;
+// One CTA per (problem, time block): BP_THREADS compute threads (8 warps) plus one producer warp.  The per-knot inputs
+// (AB, H, g: 3 KB) stream through a BP_STAGES-deep ring in shared memory filled by TMA bulk copies (cp.async.bulk +
+// mbarrier) that the producer warp keeps BP_STAGES knots ahead; it never joins the compute warps' named barrier.
+// Every knot is five barrier-separated stages on the critical path
+//     A   AB2 = AB'(P + rho I)                       147 threads, 2 outputs each
+//     B   Huu (warp 0, directly in the register layout of the elimination) -> 7x7 Gauss-Jordan in registers (shuffles),
+//         while warps 1..7 assemble the other 392 entries of H and g
+//     C   K = Huu^-1 Hux, du = Huu^-1 gu
+//     D   T = K'Huu - Hxu;  beside it A-BK, B du, KT, du -> HBM and the expected-reduction sums
+//     E   P, p of the previous knot
+// The stages are bound by shared-memory wavefronts and dependent-issue latency, not by FP32 rate, so each thread owns a
+// small tile of outputs that share operand vectors, all operands are fetched with 8/16-byte loads before the first FMA
+// (7-vectors live in rows padded to 8 floats), and lanes of a warp read either consecutive or identical rows
+// (conflict-free or broadcast).  The order of the fused multiply-adds inside every output is the reference's.
+constexpr int BP_THREADS = 256;              // compute threads; one more warp only feeds the TMA ring
+constexpr int BP_CTA = BP_THREADS + 32;
 constexpr int BP_STAGES = 4;
 template <int n, int m>
 struct __align__(16) BpSmem {
@@ -93,23 +114,36 @@ struct __align__(16) BpSmem {
     float AB[BP_STAGES][AB_STRIDE];      // ring of knot inputs
     float Hc[BP_STAGES][H_STRIDE];
     float gc[BP_STAGES][G_STRIDE];
-    unsigned long long full[BP_STAGES];
-    float P[n*n], p[n + 2];
-    float Pr[n*n];          // P + rho on the diagonal: the (P + rho I) operand of the u-rows of AB'(.) (bpHelpers.cuh:62)
-    float AB2[n*nm];        // AB'(P+rho), later K'Huu - Hxu
-    float H[nm*nm + 3], g[nm + 3];
-    float K[m*n], du[m + 1];
-    float Huu[2*m*m];
+    unsigned long long full[BP_STAGES], empty[BP_STAGES];
+    float P[n*n];                        // P[ky*n + j]
+    float Pr[n*n];                       // P + rho on the diagonal: the (P + rho I) operand of the u-rows of AB'(.) (bpHelpers.cuh:62)
+    float p[n + 2];
+    float p0[n + 2];                     // p as stage E wrote it (stage A of the next knot adds the defect term in place)
+    float AB2[nm*n + 2];                 // AB2[kx*n + ky] = sum_j AB[kx*n+j] (P+rho)[ky*n+j]   (kx < nm, ky < n)
+    float H[nm*nm + 3];                  // H[kx + nm*ky]
+    float g[nm + 3];
+    float Hux[n*8];                      // Hux[ky*8 + j] = H[(n+j) + nm*ky], rows padded to 8 floats
+    float Huu[m*8];                      // Huu[c*8 + l]  = H[(n+l) + nm*(n+c)]
+    float Hinv[m*8];                     // Hinv[l*8 + j] = (Huu^-1)(l, j)
+    float K[n*8];                        // K[ky*8 + kx]  = K(kx, ky)  (reference: K[kx + ky*m])
+    float T[n*8];                        // T[kx*8 + j]   = (K'Huu - Hxu)(kx, j)
+    float du[8];
     float dx[n + 2];
     float dJ[2*m + 2];
 };
 
-// keeps the operand loads of a chain ahead of its first FMA (all LDS in flight together)
-#define SCHED_FENCE() asm volatile("" ::: "memory")
 #ifdef PDDP_BP_TRACE
-#define BP_TRACE(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && iter >= iterCount - 7){ S.dbg[(iterCount - iter)*8 + (slot)] = clock64(); } } while (0)
+// stage clocks of thread 0 are kept in registers and written once per knot (a store in front of a stage's loads would delay them)
+#define BP_TRACE(slot) do { tr[slot] = clock64(); } while (0)
+#define BP_TRACE_DECL long long tr[12] = {0,0,0,0,0,0,0,0,0,0,0,0}
+#define BP_TRACE_FLUSH() do { if (tracer && iter >= iterCount - 7){ for (int q_ = 0; q_ < 12; q_++){ S.dbg[(iterCount - iter)*12 + q_] = tr[q_]; } } } while (0)
 #else
 #define BP_TRACE(slot) do { } while (0)
+#define BP_TRACE_DECL
+#define BP_TRACE_FLUSH() do { } while (0)
+#endif
+#ifndef PDDP_BP_SKIP
+#define PDDP_BP_SKIP 0      // timing ablations only (tools/bp_ablate.sh): bit q set = stage q's body is left out
 #endif
 
 // K-term fused chain val = sum_j a[j*sa] * b[j*sb], j ascending, operands loaded first
@@ -123,10 +157,31 @@ __device__ __forceinline__ float chain(const float *a, int sa, const float *b, i
     for (int j = 0; j < K; j++){ val = FMA(x[j], y[j], val); }
     return val;
 }
+// 14 contiguous floats at an 8-byte aligned shared address / 8 floats at a 16-byte aligned one
+__device__ __forceinline__ void ld14(float (&x)[14], const float *p){
+    const float2 *q = reinterpret_cast<const float2*>(p);
+    #pragma unroll
+    for (int i = 0; i < 7; i++){ const float2 v = q[i]; x[2*i] = v.x; x[2*i+1] = v.y; }
+}
+__device__ __forceinline__ void ld8(float (&x)[8], const float *p){
+    const float4 *q = reinterpret_cast<const float4*>(p);
+    const float4 a = q[0], b = q[1];
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+// keeps the operand loads of a tile ahead of its first FMA (all LDS in flight together)
+#define SCHED_FENCE() asm volatile("" ::: "memory")
+template <int K, int KP>
+__device__ __forceinline__ float dotr(const float (&x)[KP], const float (&y)[KP]){
+    float val = 0.f;
+    #pragma unroll
+    for (int j = 0; j < K; j++){ val = FMA(x[j], y[j], val); }
+    return val;
+}
 
 template <int n, int m>
-__global__ void __launch_bounds__(BP_THREADS, 2) bp_kernel(DevState S, int cur, int b0){
-    constexpr int nm = n + m, oHXU = n*nm, oHUU = n*nm + n, oGU = n, oB = n*n, T_ = BP_THREADS;
+__global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int b0){
+    static_assert(n == 14 && m == 7, "the thread maps of the backward pass are laid out for the 14-state, 7-control arm");
+    constexpr int nm = n + m, oB = n*n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BpSmem<n,m> &s = *reinterpret_cast<BpSmem<n,m>*>(smem_raw);
     const int b = b0 + blockIdx.x / S.M, block = blockIdx.x % S.M, t = threadIdx.x;
@@ -139,22 +194,26 @@ __global__ void __launch_bounds__(BP_THREADS, 2) bp_kernel(DevState S, int cur, 
     const bool last_block = (ks == N - 1);
     if (last_block){ ks--; iterCount = NBB - 2; } else { iterCount = NBB - 1; }
     const int nknots = iterCount + 1, ks0 = ks;                   // knots ks0, ks0-1, ... ks0-nknots+1
-    // ---- ring setup + first BP_STAGES-1 loads
+    // ---- ring setup; warp 8 is the producer: it keeps BP_STAGES knots of (AB, H, g) in flight and never joins a barrier again
     if (t == 0){
-        for (int q = 0; q < BP_STAGES; q++){ mbar_init(&s.full[q], 1); }
+        for (int q = 0; q < BP_STAGES; q++){ mbar_init(&s.full[q], 1); mbar_init(&s.empty[q], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int i){       // load knot number i (processing order) into slot i % BP_STAGES; thread 0 only
-        const int slot = i % BP_STAGES; const size_t k = bN + ks0 - i;
-        mbar_expect_tx(&s.full[slot], (AB_STRIDE + H_STRIDE + G_STRIDE)*4);
-        tma_load_1d(s.AB[slot], S.AB + k*AB_STRIDE, AB_STRIDE*4, &s.full[slot]);
-        tma_load_1d(s.Hc[slot], S.H + k*H_STRIDE, H_STRIDE*4, &s.full[slot]);
-        tma_load_1d(s.gc[slot], S.g + k*G_STRIDE, G_STRIDE*4, &s.full[slot]);
-    };
-    if (t == 0){ for (int i = 0; i < BP_STAGES-1 && i < nknots; i++){ issue(i); } }
-
-    float dJ0 = 0.f, dJ1 = 0.f;          // threads 52..58: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
+    if (t >= BP_THREADS){
+        if (t == BP_THREADS){
+            for (int i = 0; i < nknots; i++){       // knot number i (processing order) goes to slot i % BP_STAGES
+                const int slot = i % BP_STAGES; const size_t k = bN + ks0 - i;
+                if (i >= BP_STAGES){ mbar_wait_sleep(&s.empty[slot], ((i / BP_STAGES) - 1) & 1); }
+                mbar_expect_tx(&s.full[slot], (AB_STRIDE + H_STRIDE + G_STRIDE)*4);
+                tma_load_1d(s.AB[slot], S.AB + k*AB_STRIDE, AB_STRIDE*4, &s.full[slot]);
+                tma_load_1d(s.Hc[slot], S.H + k*H_STRIDE, H_STRIDE*4, &s.full[slot]);
+                tma_load_1d(s.gc[slot], S.g + k*G_STRIDE, G_STRIDE*4, &s.full[slot]);
+            }
+        }
+        return;
+    }
+    float dJ0 = 0.f, dJ1 = 0.f;          // threads 210..216: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
     if (last_block){
         // final block: Hxx[N-1] -> P[N-2], gx[N-1] -> p[N-2]  (bpHelpers.cuh:362-367)
         const size_t kN = bN + N - 1; float *gP = S.Pbuf[cur] + (kN-1)*n*n, *gp = S.pbuf[cur] + (kN-1)*n;
@@ -165,15 +224,58 @@ __global__ void __launch_bounds__(BP_THREADS, 2) bp_kernel(DevState S, int cur, 
         const float *gPp = S.Pbuf[cur^1] + (bN + ks)*n*n;
         if (t < n*n){ const float v = gPp[t]; s.P[t] = v; s.Pr[t] = (t % n == t / n) ? ADD(v, rho) : v; }
         if (t >= 224 && t < 224 + n){ const int r = t - 224; s.dx[r] = SUB(S.xp[(bN + ks + 1)*n + r], S.xp2[(bN + ks + 1)*n + r]); }
-        __syncthreads();
+        bar_sync(1, BP_THREADS);
         if (t < n){ s.p[t] = FMA(1.0f, chain<n>(&s.P[t], n, s.dx, 1), S.pbuf[cur^1][(bN + ks)*n + t]); }
     }
-    __syncthreads();
+    // ---- per-thread tile coordinates of every stage (fixed for the whole block)
+    const int a_kx = t % nm, a_kp = (t / nm) % 7;                 // stage A: (kx, ky pair), t < 147
+    const int u = t - 32;                                         // stage B, warps 1..7
+    const int b_kx = (u >= 0 ? u : 0) % nm, b_kp = ((u >= 0 ? u : 0) / nm) % 7;      // region 1: ky < n, all kx (u < 147)
+    const int b2 = (u >= 147 && u < 196) ? u - 147 : 0;           // region 2: ky >= n, kx < n (kx pairs)
+    const int b2_kxp = b2 % 7, b2_ky = n + b2 / 7;
+    const int hl = min(t & 7, 6), hg = (t & 31) >> 3;             // Huu in warp 0: lane = l + 8*(column pair)
+    const int c_kx = t % m, c_ky = (t / m) % n;                   // stage C, t < 98
+    const int d_kx = t % n, d_ky = (t / n) % m;                   // stage D, T: t < 98
+    const int dv = (t >= 32 && t < 130) ? t - 32 : 0;             // deferred A-BK: (kx, ky pair)
+    const int d2_kx = dv % n, d2_kyp = dv / n;
+    const int te = (t >= 32) ? t - 32 : 0;                        // stage E: warps 1..7 (warp 0 is the slowest to leave stage D)
+    const int e_kx = te % n, e_ky = (te / n) % n;                 // te < 196
+    // Results of a knot go to HBM one knot late, from warps 1..7 while warp 0 eliminates the next Huu: a barrier does not
+    // release before the global stores issued in front of it have been performed, which would put a memory round trip on
+    // the critical path of stages D and E.  K, du, P, p0 and the knot's ring slot are all still intact at that point.
+    auto flush_outputs = [&](size_t kp, const float *sABp, bool with_P){
+        const int u_ = t - 32;
+        if (u_ < 0){ return; }
+        if (S.M > 1){
+            if (u_ < 98){
+                float bb[8], k0[8], k1[8];
+                #pragma unroll
+                for (int j = 0; j < m; j++){ bb[j] = sABp[oB + d2_kx + n*j]; }
+                bb[7] = 0.f;
+                ld8(k0, s.K + (2*d2_kyp)*8); ld8(k1, s.K + (2*d2_kyp+1)*8);
+                const float a0 = sABp[d2_kx + n*(2*d2_kyp)], a1 = sABp[d2_kx + n*(2*d2_kyp+1)];
+                SCHED_FENCE();
+                S.ApBK[kp*n*n + d2_kx + n*(2*d2_kyp)] = SUB(a0, dotr<m>(bb, k0));
+                S.ApBK[kp*n*n + d2_kx + n*(2*d2_kyp+1)] = SUB(a1, dotr<m>(bb, k1));
+            } else if (u_ >= 196 && u_ < 196 + n){
+                const int kx = u_ - 196; S.Bdu[kp*n + kx] = chain<m>(&sABp[oB+kx], n, s.du, 1);
+            }
+        }
+        if (u_ >= 98 && u_ < 196){ const int e = u_ - 98, kx = e % n, ky = e / n; S.KT[kp*n*m + e] = s.K[kx*8 + ky]; }
+        if (u_ >= 196 + n && u_ < 196 + n + m){ const int r = u_ - (196 + n); S.du[kp*m + r] = s.du[r]; }
+        if (with_P){
+            if (u_ < n*n){ S.Pbuf[cur][(kp-1)*n*n + u_] = s.P[u_]; }
+            else if (u_ < n*n + n){ S.pbuf[cur][(kp-1)*n + u_ - n*n] = s.p0[u_ - n*n]; }
+        }
+    };
+#ifdef PDDP_BP_TRACE
+    int tracer; asm volatile("mov.u32 %0, %1;" : "=r"(tracer) : "r"((int)(blockIdx.x == 0 && threadIdx.x == PDDP_TRACE_THREAD)));
+#endif
+    bar_sync(1, BP_THREADS);
     #pragma unroll 1
     for (int iter = iterCount, i = 0; iter >= 0; iter--, ks--, i++){
         const int slot = i % BP_STAGES;
-        // refill the slot freed by the previous knot (all of its readers are past the barrier that ended that knot)
-        if (t == 0 && i + BP_STAGES - 1 < nknots){ issue(i + BP_STAGES - 1); }
+        BP_TRACE_DECL;
         BP_TRACE(0);
         mbar_wait(&s.full[slot], (i / BP_STAGES) & 1);
         BP_TRACE(1);
@@ -181,118 +283,157 @@ __global__ void __launch_bounds__(BP_THREADS, 2) bp_kernel(DevState S, int cur, 
         const size_t kk = bN + ks;
         const bool boundary = S.M > 1 && iter == NBB - 1;      // block-local defect-boundary test of the reference (bpHelpers.cuh:73)
         // ---- stage A: AB2 = AB'(P + rho I[u rows]);  p += P d on the block-local defect boundary (bpHelpers.cuh:54-81)
-        #pragma unroll
-        for (int q = 0; q < 2; q++){
-            const int e = t + T_*q;
-            if (e < n*nm){
-                // x-rows use P (the reference adds +0, an identity), u-rows use P + rho on the diagonal
-                const int ky = e / nm, kx = e % nm;
-                s.AB2[ky*nm+kx] = chain<n>(&sAB[kx*n], 1, (kx >= n ? s.Pr : s.P) + ky*n, 1);
-            } else if (e < n*nm + n){
-                const int r = e - n*nm; float val = 0.f;
-                if (boundary){ val = chain<n>(S.dp + kk*n, 1, &s.P[r], n); }
-                s.p[r] = ADD(s.p[r], val);
-            }
+        if (PDDP_BP_SKIP & 1){ } else
+        if (t < 147){
+            // x-rows use P (the reference adds +0, an identity), u-rows use P + rho on the diagonal
+            float x[14], y0[14], y1[14];
+            const float *Pq = (a_kx >= n) ? s.Pr : s.P;
+            ld14(x, sAB + a_kx*n); ld14(y0, Pq + (2*a_kp)*n); ld14(y1, Pq + (2*a_kp+1)*n);
+            SCHED_FENCE();
+            float v0 = 0.f, v1 = 0.f;
+            #pragma unroll
+            for (int j = 0; j < n; j++){ v0 = FMA(x[j], y0[j], v0); v1 = FMA(x[j], y1[j], v1); }
+            *reinterpret_cast<float2*>(&s.AB2[a_kx*n + 2*a_kp]) = make_float2(v0, v1);
+        } else if (t >= 224 && t < 224 + n){
+            const int r = t - 224; float val = 0.f;
+            if (boundary){ val = chain<n>(S.dp + kk*n, 1, &s.P[r], n); }
+            s.p[r] = ADD(s.p[r], val);
         }
-        __syncthreads();
+        bar_sync(1, BP_THREADS);
         BP_TRACE(2);
-        // ---- stage B1: first half of H = (AB2 AB)' + H_cost: threads 0..48 take the Huu block (needed first), the others
-        //      the start of the remaining 392 entries and g
-        {
-            if (t < m*m){
-                const int ky = n + t / m, kx = n + t % m;
-                const float h = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
-                s.H[kx+nm*ky] = h;
-                s.Huu[(kx-n) + m*(ky-n)] = MUL(1.0f, h); s.Huu[m*m + (ky-n)*m + (kx-n)] = (kx == ky) ? 1.f : 0.f;
-            } else {
-                const int item = t - m*m;                         // 0 .. 206
-                int kx, ky;
-                if (item < n*nm){ ky = item / nm; kx = item % nm; } else { const int r = item - n*nm; ky = n + r / n; kx = r % n; }
-                s.H[kx+nm*ky] = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
-            }
-        }
-        __syncthreads();
-        BP_TRACE(3);
-        // ---- stage B2: warp 0 inverts Huu in registers while warps 1..7 finish H and g
+        // ---- stage B: H = (AB2 AB)' + H_cost, g = AB'p + g_cost (bpHelpers.cuh:83-118); Huu^-1 (invHelpers.cuh)
+        if ((PDDP_BP_SKIP & 4) && t < 32){ } else if ((PDDP_BP_SKIP & 2) && t >= 32){ } else
         if (t < 32){
-            gauss_jordan_group<m, 32>(s.Huu);
-            BP_TRACE(4);
-        } else {
-            const int item = (T_ - m*m) + (t - 32);               // 207 .. 430
-            if (item < nm*nm - m*m){
-                int kx, ky;
-                if (item < n*nm){ ky = item / nm; kx = item % nm; } else { const int r = item - n*nm; ky = n + r / n; kx = r % n; }
-                s.H[kx+nm*ky] = FMA(1.0f, chain<n>(&s.AB2[ky], nm, &sAB[kx*n], 1), MUL(1.0f, bH[kx+nm*ky]));
-            } else if (item < nm*nm - m*m + nm){
-                const int r = item - (nm*nm - m*m);
-                s.g[r] = FMA(1.0f, chain<n>(s.p, 1, &sAB[r*n], 1), MUL(1.0f, bg[r]));
+            // lane l + 8*q computes Huu(l, 2q) and Huu(l, 2q+1); the rows are then gathered on lanes 0..6
+            float x[14], y0[14], y1[14];
+            const int c0 = min(2*hg, 6), c1 = min(2*hg + 1, 6);
+            ld14(x, sAB + (n + hl)*n); ld14(y0, s.AB2 + (n + c0)*n); ld14(y1, s.AB2 + (n + c1)*n);
+            const float q0 = bH[(n + hl) + nm*(n + c0)], q1 = bH[(n + hl) + nm*(n + c1)];
+            SCHED_FENCE();
+            float v0 = 0.f, v1 = 0.f;
+            #pragma unroll
+            for (int j = 0; j < n; j++){ v0 = FMA(y0[j], x[j], v0); v1 = FMA(y1[j], x[j], v1); }
+            const float h0 = FMA(1.0f, v0, MUL(1.0f, q0)), h1 = FMA(1.0f, v1, MUL(1.0f, q1));
+            if ((t & 7) < 7){
+                s.H[(n + hl) + nm*(n + c0)] = h0; s.Huu[c0*8 + hl] = h0;
+                if (2*hg + 1 < m){ s.H[(n + hl) + nm*(n + c1)] = h1; s.Huu[c1*8 + hl] = h1; }
             }
+            float a[2*m];
+            #pragma unroll
+            for (int c = 0; c < m; c++){ a[c] = MUL(1.0f, __shfl_sync(FULL, (c & 1) ? h1 : h0, (t & 7) + 8*(c >> 1))); a[m + c] = (t == c) ? 1.f : 0.f; }
+            BP_TRACE(3);
+            gauss_jordan_rows<m>(a, t);
+            if (t < m){
+                *reinterpret_cast<float4*>(&s.Hinv[t*8]) = make_float4(a[m], a[m+1], a[m+2], a[m+3]);
+                *reinterpret_cast<float4*>(&s.Hinv[t*8 + 4]) = make_float4(a[m+4], a[m+5], a[m+6], 0.f);
+            }
+            BP_TRACE(4);
+        } else if (u < 147){
+            float x[14], y0[14], y1[14];
+            ld14(x, sAB + b_kx*n); ld14(y0, s.AB2 + (2*b_kp)*n); ld14(y1, s.AB2 + (2*b_kp+1)*n);
+            const float q0 = bH[b_kx + nm*(2*b_kp)], q1 = bH[b_kx + nm*(2*b_kp+1)];
+            SCHED_FENCE();
+            float v0 = 0.f, v1 = 0.f;
+            #pragma unroll
+            for (int j = 0; j < n; j++){ v0 = FMA(y0[j], x[j], v0); v1 = FMA(y1[j], x[j], v1); }
+            const float h0 = FMA(1.0f, v0, MUL(1.0f, q0)), h1 = FMA(1.0f, v1, MUL(1.0f, q1));
+            s.H[b_kx + nm*(2*b_kp)] = h0; s.H[b_kx + nm*(2*b_kp+1)] = h1;
+            if (b_kx >= n){ s.Hux[(2*b_kp)*8 + b_kx - n] = h0; s.Hux[(2*b_kp+1)*8 + b_kx - n] = h1; }
+        } else if (u < 196){
+            float y[14], x0[14], x1[14];
+            ld14(y, s.AB2 + b2_ky*n); ld14(x0, sAB + (2*b2_kxp)*n); ld14(x1, sAB + (2*b2_kxp+1)*n);
+            const float q0 = bH[2*b2_kxp + nm*b2_ky], q1 = bH[2*b2_kxp + 1 + nm*b2_ky];
+            SCHED_FENCE();
+            float v0 = 0.f, v1 = 0.f;
+            #pragma unroll
+            for (int j = 0; j < n; j++){ v0 = FMA(y[j], x0[j], v0); v1 = FMA(y[j], x1[j], v1); }
+            s.H[2*b2_kxp + nm*b2_ky] = FMA(1.0f, v0, MUL(1.0f, q0)); s.H[2*b2_kxp + 1 + nm*b2_ky] = FMA(1.0f, v1, MUL(1.0f, q1));
+        } else if (u < 196 + nm){
+            const int r = u - 196;
+            float x[14], y[14];
+            ld14(x, s.p); ld14(y, sAB + r*n);
+            s.g[r] = FMA(1.0f, dotr<n>(x, y), MUL(1.0f, bg[r]));
         }
-        __syncthreads();
+        if (i > 0){ flush_outputs(kk + 1, s.AB[(i - 1) % BP_STAGES], true); }
+        bar_sync(1, BP_THREADS);
         BP_TRACE(5);
-        const float *Hinv = &s.Huu[m*m];
         // ---- stage C: K = Huu^-1 Hux, du = Huu^-1 gu (bpHelpers.cuh:206-220)
+        if (PDDP_BP_SKIP & 8){ } else
         if (t < n*m){
-            const int ky = t / m, kx = t % m;
-            s.K[kx+ky*m] = MUL(1.0f, chain<m>(&Hinv[kx], m, &s.H[oGU + ky*nm], 1));
+            float hi[8], hx[8];
+            ld8(hi, s.Hinv + c_kx*8); ld8(hx, s.Hux + c_ky*8);
+            s.K[c_ky*8 + c_kx] = MUL(1.0f, dotr<m>(hi, hx));
         } else if (t >= 128 && t < 128 + m){
             const int r = t - 128;
-            s.du[r] = ADD(MUL(1.0f, chain<m>(&Hinv[r], m, &s.g[oGU], 1)), 0.f);
+            float hi[8], gu[8];
+            ld8(hi, s.Hinv + r*8);
+            #pragma unroll
+            for (int j = 0; j < m; j++){ gu[j] = s.g[n + j]; }
+            gu[7] = 0.f;
+            s.du[r] = ADD(MUL(1.0f, dotr<m>(hi, gu)), 0.f);
         }
-        __syncthreads();
+        bar_sync(1, BP_THREADS);
         BP_TRACE(6);
-        // ---- stage D: T = K'Huu - Hxu (into AB2), A-BK, B du, expected reduction, KT/du to HBM
+        // ---- stage D: T = K'Huu - Hxu; A-BK, B du, KT, du to HBM; expected reduction (bpHelpers.cuh:223-240,282-331)
         const bool do_ctg = (iter != 0 || block != 0);
-        #pragma unroll
-        for (int q = 0; q < 2; q++){
-            const int e = t + T_*q;
-            if (e < n*m){
-                if (do_ctg){ const int ky = e / n, kx = e % n; s.AB2[kx+ky*n] = SUB(chain<m>(&s.K[kx*m], 1, &s.H[oHUU+ky*nm], 1), s.H[oHXU+kx+nm*ky]); }
-            } else if (e < n*m + n*n){
-                if (S.M > 1){ const int r = e - n*m, ky = r / n, kx = r % n; S.ApBK[kk*n*n + kx + n*ky] = SUB(sAB[kx+n*ky], chain<m>(&sAB[oB+kx], n, &s.K[ky*m], 1)); }
-            } else if (e < n*m + n*n + n){
-                if (S.M > 1){ const int kx = e - n*m - n*n; S.Bdu[kk*n + kx] = chain<m>(&sAB[oB+kx], n, s.du, 1); }
-            } else if (e < n*m + n*n + n + m){
-                const int ind = e - (n*m + n*n + n);
-                const float dot = chain<m>(&s.H[oHUU+ind], nm, s.du, 1);
-                dJ0 = FMA(s.du[ind], s.g[oGU+ind], dJ0); dJ1 = FMA(s.du[ind], dot, dJ1);
-            } else if (e < n*m + n*n + n + m + n*m){
-                const int r = e - (n*m + n*n + n + m), ky = r / n, kx = r % n;
-                S.KT[kk*n*m + kx + n*ky] = s.K[ky + m*kx];
-            } else if (e < n*m + n*n + n + m + n*m + m){
-                const int r = e - (n*m + n*n + n + m + n*m); S.du[kk*m + r] = s.du[r];
+        if (PDDP_BP_SKIP & 16){ } else
+        if (t < n*m){
+            if (do_ctg){
+                float k[8], h[8];
+                ld8(k, s.K + d_kx*8); ld8(h, s.Huu + d_ky*8);
+                const float hxu = s.H[d_kx + nm*(n + d_ky)];
+                s.T[d_kx*8 + d_ky] = SUB(dotr<m>(k, h), hxu);
             }
+        } else if (t >= 196 + n && t < 196 + n + m){
+            const int ind = t - (196 + n);
+            float h[m];
+            #pragma unroll
+            for (int j = 0; j < m; j++){ h[j] = s.Huu[j*8 + ind]; }
+            float dot = 0.f;
+            #pragma unroll
+            for (int j = 0; j < m; j++){ dot = FMA(h[j], s.du[j], dot); }
+            dJ0 = FMA(s.du[ind], s.g[n + ind], dJ0); dJ1 = FMA(s.du[ind], dot, dJ1);
         }
-        __syncthreads();
+        bar_sync(1, BP_THREADS);
         BP_TRACE(7);
-        // ---- stage E: cost-to-go of the previous knot (bpHelpers.cuh:223-276)
-        if (do_ctg){
-            if (t < n*n){
-                const int ky = t / n, kx = t % n;
-                float a[m], c[m], k2[m], h2[m];
-                #pragma unroll
-                for (int j = 0; j < m; j++){ a[j] = s.AB2[kx+n*j]; c[j] = s.K[ky*m+j]; k2[j] = s.K[kx*m+j]; h2[j] = s.H[oGU+ky*nm+j]; }
+        // ---- stage E: cost-to-go of the previous knot (bpHelpers.cuh:242-276)
+        if (do_ctg && !(PDDP_BP_SKIP & 32)){
+            if (t >= 32 && t < 32 + n*n){
+                float a[8], c[8], k2[8], h2[8];
+                ld8(a, s.T + e_kx*8); ld8(c, s.K + e_ky*8); ld8(k2, s.K + e_kx*8); ld8(h2, s.Hux + e_ky*8);
+                const float hxx = s.H[e_kx + e_ky*nm];
+                SCHED_FENCE();
                 float val = 0.f;
                 #pragma unroll
                 for (int j = 0; j < m; j++){ val = ADD(val, FMA(a[j], c[j], -MUL(k2[j], h2[j]))); }
-                const float v = ADD(s.H[kx+ky*nm], val);
-                s.P[t] = v; s.Pr[t] = (kx == ky) ? ADD(v, rho) : v; S.Pbuf[cur][(kk-1)*n*n + t] = v;
-            } else if (t >= 224 && t < 224 + n){
-                const int r = t - 224; float val = 0.f;
+                const float v = ADD(hxx, val);
+#ifdef PDDP_BP_TRACE
+                if (v == 1.2345e-30f){ S.dbg[4000] = 1; }
+                BP_TRACE(10);
+#endif
+                s.P[te] = v; s.Pr[te] = (e_kx == e_ky) ? ADD(v, rho) : v;
+                BP_TRACE(11);
+            } else if (t >= 228 && t < 228 + n){
+                const int r = t - 228;
+                float a[8], k2[8];
+                ld8(a, s.T + r*8); ld8(k2, s.K + r*8);
+                float val = 0.f;
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], s.AB2[r+n*j], -MUL(s.K[r*m+j], s.g[oGU+j]))); }
+                for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], a[j], -MUL(k2[j], s.g[n + j]))); }
                 const float v = ADD(s.g[r], val);
-                s.p[r] = v; S.pbuf[cur][(kk-1)*n + r] = v;
+                s.p[r] = v; s.p0[r] = v;
             }
         }
-        __syncthreads();      // P,p of the next knot are complete; the ring slot of this knot is free
+        BP_TRACE(8);
+        bar_sync(1, BP_THREADS);      // P,p of the next knot are complete
+        BP_TRACE(9);
+        BP_TRACE_FLUSH();
+        if (t == 0 && i > 0){ mbar_arrive(&s.empty[(i - 1) % BP_STAGES]); }      // the previous knot's ring slot (its deferred stores are done) goes back to the producer
     }
+    flush_outputs(bN + ks + 1, s.AB[(nknots - 1) % BP_STAGES], block != 0);      // the last knot of the block (block 0 ends without a cost-to-go)
     // ---- expected cost reduction of this block: thread 0 sums the m per-thread partials in order (bpHelpers.cuh:416)
-    {
-        const int e = t + T_, base = n*m + n*n + n;
-        if (e >= base && e < base + m){ s.dJ[e-base] = dJ0; s.dJ[m + e-base] = dJ1; }
-    }
-    __syncthreads();
+    if (t >= 196 + n && t < 196 + n + m){ s.dJ[t - (196 + n)] = dJ0; s.dJ[m + t - (196 + n)] = dJ1; }
+    bar_sync(1, BP_THREADS);
     if (t == 0){
         float a0 = s.dJ[0], a1 = s.dJ[m];
         for (int j = 1; j < m; j++){ a0 = ADD(a0, s.dJ[j]); a1 = ADD(a1, s.dJ[m+j]); }

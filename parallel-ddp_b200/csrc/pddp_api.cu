@@ -188,7 +188,7 @@ static int launch_init(pddp_handle h){       // initAlgGPU (nisInitHelpers.cuh:3
 // problems [b0, b0+nb) on stream st
 static int launch_bp(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_THREADS, h->smem_bp, st>>>(S, h->cur, b0);
+    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_CTA, h->smem_bp, st>>>(S, h->cur, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
@@ -317,6 +317,27 @@ extern "C" int pddp_solve(pddp_handle h, const float *x0, const float *u0, const
     return 0;
 }
 
+namespace pddp {
+__global__ void selftest_rcp_kernel(unsigned long long *bad){
+    unsigned long long local = 0;
+    for (unsigned long long v = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; v < (1ull << 32); v += (unsigned long long)gridDim.x*blockDim.x){
+        const float x = __uint_as_float((unsigned)v);
+        const float a = rcp_rn(x), b = __fdiv_rn(1.0f, x);
+        const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+        local += same ? 0 : 1;
+    }
+    if (local){ atomicAdd(bad, local); }
+}
+}
+extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
+    if (!mismatches){ return PDDP_E_INVALID; }
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess || cudaMemset(d, 0, 8) != cudaSuccess){ return PDDP_E_CUDA; }
+    pddp::selftest_rcp_kernel<<<148*8, 256>>>(d);
+    const cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : PDDP_E_CUDA;
+}
 extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
 extern "C" int pddp_set_groups(pddp_handle h, int groups){
     if (!h || groups < 1 || groups > 8){ return PDDP_E_INVALID; }
