@@ -2,6 +2,8 @@
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pddp = importlib.import_module("parallel-ddp_b200")
+if os.environ.get("PDDP_LIB"):
+    pddp.LIB_PATH = os.path.abspath(os.environ["PDDP_LIB"])
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 N = 128
