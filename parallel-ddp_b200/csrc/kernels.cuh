@@ -493,7 +493,12 @@ constexpr int SIM_LANES = 16;
 struct SimGroupSmem {
     kuka::FwdWsT<false> ws;
     float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
+#ifndef PDDP_SIM_PAD
+#define PDDP_SIM_PAD 14
+#endif
+    float pad[PDDP_SIM_PAD];   // the two groups of a warp sit 16 banks apart
 };
+static_assert(sizeof(SimGroupSmem) % 16 == 0 || PDDP_SIM_PAD != 14, "group workspace must stay float4-aligned");
 
 // joint-space quadratic cost of one knot (plants/cost_arm.cuh:128-153), evaluated by one lane
 __device__ __forceinline__ float cost_knot(const float *x, const float *u, const float *xg, bool final_knot, const DevState &S){
@@ -527,6 +532,7 @@ __global__ void sim_kernel(DevState S, int b0){
     if (!live){ a = S.A - 1; }
     SimGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb);
+    const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
     const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (w < S.M - 1) ? NBF : NBF - 1;
     const float alpha = S.alpha[a], dt = S.dt;
     float *gx = S.x + ((size_t)b*S.A + a)*N*n, *gu = S.u + ((size_t)b*S.A + a)*N*m, *gdd = S.d + ((size_t)b*S.A + a)*N*n;
@@ -566,7 +572,7 @@ __global__ void sim_kernel(DevState S, int b0){
             s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
         }
         __syncwarp();
-        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd);
+        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
         __syncwarp();
@@ -758,11 +764,12 @@ __global__ void unit_dynamics_kernel(const float *I, const float *Tbody, const f
     __syncthreads();
     SimGroupSmem &s = gsm[grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb);
+    const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
     for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
         const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;         // tail: replay the last sample
         if (l < kuka::NX){ s.x[l] = x[k*kuka::NX + l]; } if (l < kuka::NU){ s.u[l] = u[k*kuka::NU + l]; }
         __syncwarp();
-        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd);
+        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
         if (l < kuka::NB){ qdd[k*kuka::NB + l] = s.qdd[l]; }
         __syncwarp();
     }
