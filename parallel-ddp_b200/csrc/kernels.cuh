@@ -490,15 +490,15 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
 // half-warp (SIM_LANES = 16 lanes cooperate on one trajectory; both halves run the same instruction stream).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SIM_LANES = 16;
-struct SimGroupSmem {
+struct SimGroupData {
     kuka::FwdWsT<false> ws;
     float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
-#ifndef PDDP_SIM_PAD
-#define PDDP_SIM_PAD 14
-#endif
-    float pad[PDDP_SIM_PAD];   // the two groups of a warp sit 16 banks apart
 };
-static_assert(sizeof(SimGroupSmem) % 16 == 0 || PDDP_SIM_PAD != 14, "group workspace must stay float4-aligned");
+// The two groups of a warp run the same instruction on their own workspaces: the workspaces are padded to an odd multiple
+// of 16 banks so that a 16-lane unit-stride access of one group never meets the other group's banks.
+constexpr int SIM_GROUP_FLOATS = (int)(sizeof(SimGroupData) / 4), SIM_PAD = (48 - SIM_GROUP_FLOATS % 32) % 32;
+struct SimGroupSmem : SimGroupData { float pad[SIM_PAD ? SIM_PAD : 32]; };
+static_assert((sizeof(SimGroupSmem) / 4) % 32 == 16, "group workspaces must sit 16 banks apart");
 
 // joint-space quadratic cost of one knot (plants/cost_arm.cuh:128-153), evaluated by one lane
 __device__ __forceinline__ float cost_knot(const float *x, const float *u, const float *xg, bool final_knot, const DevState &S){
