@@ -684,18 +684,29 @@ struct NisGroupSmem {
     kuka::FwdWs ws; kuka::GradWs gs;
     float x[16], u[8], qdd[8], dqdd[3*kuka::NB*kuka::NB + 1];
 };
-constexpr int NIS_WARPS = 1;
+#ifndef PDDP_NIS_WARPS
+#define PDDP_NIS_WARPS 1
+#endif
+#ifndef PDDP_NIS_STAGE
+#define PDDP_NIS_STAGE 0      // 1: body inertias / joint frames staged in shared memory per CTA, 0: read through L1 (measured faster: one more CTA per SM)
+#endif
+constexpr int NIS_WARPS = PDDP_NIS_WARPS;
+constexpr int NIS_CONST_FLOATS = PDDP_NIS_STAGE ? 2*36*kuka::NB : 0;
 
 __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode, int write_H, int b0, int nb){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, nm = n + m, np = kuka::NB, LANES = NIS_LANES, GPW = 32 / NIS_LANES;
-    float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-    NisGroupSmem *gsm = reinterpret_cast<NisGroupSmem*>(sTb + 36*kuka::NB);
+    NisGroupSmem *gsm = reinterpret_cast<NisGroupSmem*>(reinterpret_cast<float*>(smem_raw) + NIS_CONST_FLOATS);
     const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     const int gk = (blockIdx.x*NIS_WARPS + w)*GPW + grp, N = S.N;        // N is even: the groups of one warp share the problem
     const int b = b0 + gk / N, k = gk % N;
+#if PDDP_NIS_STAGE
+    float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
     __syncthreads();
+#else
+    const float *sI = S.I, *sTb = S.Tbody;
+#endif
     if (b >= b0 + nb || S.done[b]){ return; }
     NisGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, &s.gs, sTb);

@@ -124,7 +124,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     h->smem_sweep = ((size_t)(N-1)*n*n + (size_t)(N-1)*n + (size_t)2*N*n)*sizeof(float);
     h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
-    h->smem_nis = 2*36*kuka::NB*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
+    h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
     h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
     if (h->smem_sweep > 227*1024){ h->err = "N too large for the single-pass sweep staging"; return bail(PDDP_E_INVALID); }
