@@ -544,9 +544,9 @@ __global__ void sim_kernel(DevState S, int b0){
     constexpr int KTQ = (n*m + LANES - 1) / LANES;
     float rKT[KTQ], rdu = 0.f, rxp = 0.f, rup = 0.f;
     #pragma unroll
-    for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = (i < n*m) ? gKT[(size_t)kStart*n*m + i] : 0.f; }
-    if (l < m){ rdu = gdu[kStart*m + l]; rup = gup[kStart*m + l]; }
-    if (l < n){ rxp = gxp[kStart*n + l]; }
+    for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = gKT[(size_t)kStart*n*m + (i < n*m ? i : n*m - 1)]; }
+    rdu = gdu[kStart*m + (l < m ? l : m - 1)]; rup = gup[kStart*m + (l < m ? l : m - 1)];
+    rxp = gxp[kStart*n + (l < n ? l : n - 1)];
     __syncwarp();
     #pragma unroll 1
     for (int kk = 0; kk < iters; kk++){
@@ -556,11 +556,14 @@ __global__ void sim_kernel(DevState S, int b0){
         for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; if (i < n*m){ s.KT[i] = rKT[q]; } }
         if (l < n){ s.dx[l] = SUB(s.x[l], rxp); }
         const float du_k = rdu, up_k = rup;
-        if (kk + 1 < iters){
+        {
+            // unconditional, index-clamped loads straight into the loop-carried registers: a predicated load would be
+            // followed by a register move that waits for it, which exposes the global-memory latency in every step
+            const int kn = (kk + 1 < iters) ? k + 1 : k;
             #pragma unroll
-            for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = (i < n*m) ? gKT[(size_t)(k+1)*n*m + i] : 0.f; }
-            if (l < m){ rdu = gdu[(k+1)*m + l]; rup = gup[(k+1)*m + l]; }
-            if (l < n){ rxp = gxp[(k+1)*n + l]; }
+            for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = gKT[(size_t)kn*n*m + (i < n*m ? i : n*m - 1)]; }
+            rdu = gdu[kn*m + (l < m ? l : m - 1)]; rup = gup[kn*m + (l < m ? l : m - 1)];
+            rxp = gxp[kn*n + (l < n ? l : n - 1)];
         }
         __syncwarp();
         // u = up - (alpha du + K dx)          (fpHelpers.cuh:210-219)
