@@ -49,16 +49,6 @@ struct DevState {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// async staging helpers (LDGSTS): tiles are not 16-byte aligned in the reference layout (14*21 floats), so 4-byte copies
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc){
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit(){ asm volatile("cp.async.commit_group;\n" ::); }
-template <int N_> __device__ __forceinline__ void cp_async_wait(){ asm volatile("cp.async.wait_group %0;\n" :: "n"(N_)); }
-
-// ------------------------------------------------------------------------------------------------------------------
 // TMA (1-D bulk copy) + mbarrier helpers
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p){ return (unsigned)__cvta_generic_to_shared(p); }
