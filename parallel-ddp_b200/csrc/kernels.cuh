@@ -98,6 +98,9 @@ __device__ __forceinline__ void bar_sync(int id, int count){ asm volatile("bar.s
 constexpr int BP_THREADS = 256;              // compute threads; one more warp only feeds the TMA ring
 constexpr int BP_CTA = BP_THREADS + 32;
 constexpr int BP_STAGES = 4;
+// 7-vectors (rows of K, T, Hux, Huu, Hinv) are read as two 16-byte loads; rows 12 floats apart put the 8 lanes of a quarter
+// warp on 8 disjoint bank quads (rows 8 floats apart collide two by two)
+constexpr int BP_RS = 12;
 template <int n, int m>
 struct __align__(16) BpSmem {
     static constexpr int nm = n + m;
@@ -112,11 +115,11 @@ struct __align__(16) BpSmem {
     float AB2[nm*n + 2];                 // AB2[kx*n + ky] = sum_j AB[kx*n+j] (P+rho)[ky*n+j]   (kx < nm, ky < n)
     float H[nm*nm + 3];                  // H[kx + nm*ky]
     float g[nm + 3];
-    float Hux[n*8];                      // Hux[ky*8 + j] = H[(n+j) + nm*ky], rows padded to 8 floats
-    float Huu[m*8];                      // Huu[c*8 + l]  = H[(n+l) + nm*(n+c)]
-    float Hinv[m*8];                     // Hinv[l*8 + j] = (Huu^-1)(l, j)
-    float K[n*8];                        // K[ky*8 + kx]  = K(kx, ky)  (reference: K[kx + ky*m])
-    float T[n*8];                        // T[kx*8 + j]   = (K'Huu - Hxu)(kx, j)
+    float Hux[n*BP_RS];                      // Hux[ky*BP_RS + j] = H[(n+j) + nm*ky], rows of 7 in BP_RS floats
+    float Huu[m*BP_RS];                      // Huu[c*BP_RS + l]  = H[(n+l) + nm*(n+c)]
+    float Hinv[m*BP_RS];                     // Hinv[l*BP_RS + j] = (Huu^-1)(l, j)
+    float K[n*BP_RS];                        // K[ky*BP_RS + kx]  = K(kx, ky)  (reference: K[kx + ky*m])
+    float T[n*BP_RS];                        // T[kx*BP_RS + j]   = (K'Huu - Hxu)(kx, j)
     float du[8];
     float dx[n + 2];
     float dJ[2*m + 2];
@@ -218,10 +221,13 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
         if (t < n){ s.p[t] = FMA(1.0f, chain<n>(&s.P[t], n, s.dx, 1), S.pbuf[cur^1][(bN + ks)*n + t]); }
     }
     // ---- per-thread tile coordinates of every stage (fixed for the whole block)
-    const int a_kx = t % nm, a_kp = (t / nm) % 7;                 // stage A: (kx, ky pair), t < 147
+    // stage A, t < 56: column groups {0-2},{3-5},{6-8},{9-11},{12,13} | {14-16},{17-19},{20} x 7 row pairs
+    const int a_g = t & 7, a_kp = (t >> 3) % 7;
+    const int a_kx0 = a_g < 5 ? 3*a_g : n + 3*(a_g - 5), a_cnt = (a_g == 4) ? 2 : (a_g == 7 ? 1 : 3);
+    const int a_kx1 = a_cnt > 1 ? a_kx0 + 1 : a_kx0, a_kx2 = a_cnt > 2 ? a_kx0 + 2 : a_kx0;
     const int u = t - 32;                                         // stage B, warps 1..7
-    const int b_kx = (u >= 0 ? u : 0) % nm, b_kp = ((u >= 0 ? u : 0) / nm) % 7;      // region 1: ky < n, all kx (u < 147)
-    const int b2 = (u >= 147 && u < 196) ? u - 147 : 0;           // region 2: ky >= n, kx < n (kx pairs)
+    const int b_kxt = (u >= 0 ? u : 0) % 7, b_kp = ((u >= 0 ? u : 0) / 7) % 7;      // region 1: rows < n, all columns: (column triple, row pair), u < 49
+    const int b2 = (u >= 64 && u < 113) ? u - 64 : 0;             // region 2: rows >= n, columns < n (column pairs)
     const int b2_kxp = b2 % 7, b2_ky = n + b2 / 7;
     const int hl = min(t & 7, 6), hg = (t & 31) >> 3;             // Huu in warp 0: lane = l + 8*(column pair)
     const int c_kx = t % m, c_ky = (t / m) % n;                   // stage C, t < 98
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
     const int dv = (t >= 32 && t < 130) ? t - 32 : 0;             // deferred A-BK: (kx, ky pair)
     const int d2_kx = dv % n, d2_kyp = dv / n;
     const int te = (t >= 32) ? t - 32 : 0;                        // stage E: warps 1..7 (warp 0 is the slowest to leave stage D)
-    const int e_kx = te % n, e_ky = (te / n) % n;                 // te < 196
+    const int e_kxp = te % 7, e_kyp = (te / 7) % 7;               // 2 x 2 tiles of P, te < 49
     // Results of a knot go to HBM one knot late, from warps 1..7 while warp 0 eliminates the next Huu: a barrier does not
     // release before the global stores issued in front of it have been performed, which would put a memory round trip on
     // the critical path of stages D and E.  K, du, P, p0 and the knot's ring slot are all still intact at that point.
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
                 #pragma unroll
                 for (int j = 0; j < m; j++){ bb[j] = sABp[oB + d2_kx + n*j]; }
                 bb[7] = 0.f;
-                ld8(k0, s.K + (2*d2_kyp)*8); ld8(k1, s.K + (2*d2_kyp+1)*8);
+                ld8(k0, s.K + (2*d2_kyp)*BP_RS); ld8(k1, s.K + (2*d2_kyp+1)*BP_RS);
                 const float a0 = sABp[d2_kx + n*(2*d2_kyp)], a1 = sABp[d2_kx + n*(2*d2_kyp+1)];
                 SCHED_FENCE();
                 S.ApBK[kp*n*n + d2_kx + n*(2*d2_kyp)] = SUB(a0, dotr<m>(bb, k0));
@@ -251,7 +257,7 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
                 const int kx = u_ - 196; S.Bdu[kp*n + kx] = chain<m>(&sABp[oB+kx], n, s.du, 1);
             }
         }
-        if (u_ >= 98 && u_ < 196){ const int e = u_ - 98, kx = e % n, ky = e / n; S.KT[kp*n*m + e] = s.K[kx*8 + ky]; }
+        if (u_ >= 98 && u_ < 196){ const int e = u_ - 98, kx = e % n, ky = e / n; S.KT[kp*n*m + e] = s.K[kx*BP_RS + ky]; }
         if (u_ >= 196 + n && u_ < 196 + n + m){ const int r = u_ - (196 + n); S.du[kp*m + r] = s.du[r]; }
         if (with_P){
             if (u_ < n*n){ S.Pbuf[cur][(kp-1)*n*n + u_] = s.P[u_]; }
@@ -274,16 +280,25 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
         const bool boundary = S.M > 1 && iter == NBB - 1;      // block-local defect-boundary test of the reference (bpHelpers.cuh:73)
         // ---- stage A: AB2 = AB'(P + rho I[u rows]);  p += P d on the block-local defect boundary (bpHelpers.cuh:54-81)
         if (PDDP_BP_SKIP & 1){ } else
-        if (t < 147){
-            // x-rows use P (the reference adds +0, an identity), u-rows use P + rho on the diagonal
-            float x[14], y0[14], y1[14];
-            const float *Pq = (a_kx >= n) ? s.Pr : s.P;
-            ld14(x, sAB + a_kx*n); ld14(y0, Pq + (2*a_kp)*n); ld14(y1, Pq + (2*a_kp+1)*n);
+        if (t < 56){
+            // tile = (group of up to 3 columns kx of AB) x (2 rows ky of P): 5 operand vectors for 6 outputs.  The column
+            // groups do not straddle the x/u boundary: x-rows use P (the reference adds +0, an identity), u-rows use P + rho
+            // on the diagonal.
+            float x0[14], x1[14], x2[14], y0[14], y1[14];
+            const float *Pq = (a_kx0 >= n) ? s.Pr : s.P;
+            ld14(x0, sAB + a_kx0*n); ld14(x1, sAB + a_kx1*n); ld14(x2, sAB + a_kx2*n);
+            ld14(y0, Pq + (2*a_kp)*n); ld14(y1, Pq + (2*a_kp+1)*n);
             SCHED_FENCE();
-            float v0 = 0.f, v1 = 0.f;
+            float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f, v20 = 0.f, v21 = 0.f;
             #pragma unroll
-            for (int j = 0; j < n; j++){ v0 = FMA(x[j], y0[j], v0); v1 = FMA(x[j], y1[j], v1); }
-            *reinterpret_cast<float2*>(&s.AB2[a_kx*n + 2*a_kp]) = make_float2(v0, v1);
+            for (int j = 0; j < n; j++){
+                v00 = FMA(x0[j], y0[j], v00); v01 = FMA(x0[j], y1[j], v01);
+                v10 = FMA(x1[j], y0[j], v10); v11 = FMA(x1[j], y1[j], v11);
+                v20 = FMA(x2[j], y0[j], v20); v21 = FMA(x2[j], y1[j], v21);
+            }
+            *reinterpret_cast<float2*>(&s.AB2[a_kx0*n + 2*a_kp]) = make_float2(v00, v01);
+            if (a_cnt > 1){ *reinterpret_cast<float2*>(&s.AB2[a_kx1*n + 2*a_kp]) = make_float2(v10, v11); }
+            if (a_cnt > 2){ *reinterpret_cast<float2*>(&s.AB2[a_kx2*n + 2*a_kp]) = make_float2(v20, v21); }
         } else if (t >= 224 && t < 224 + n){
             const int r = t - 224; float val = 0.f;
             if (boundary){ val = chain<n>(S.dp + kk*n, 1, &s.P[r], n); }
@@ -305,8 +320,8 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
             for (int j = 0; j < n; j++){ v0 = FMA(y0[j], x[j], v0); v1 = FMA(y1[j], x[j], v1); }
             const float h0 = FMA(1.0f, v0, MUL(1.0f, q0)), h1 = FMA(1.0f, v1, MUL(1.0f, q1));
             if ((t & 7) < 7){
-                s.H[(n + hl) + nm*(n + c0)] = h0; s.Huu[c0*8 + hl] = h0;
-                if (2*hg + 1 < m){ s.H[(n + hl) + nm*(n + c1)] = h1; s.Huu[c1*8 + hl] = h1; }
+                s.H[(n + hl) + nm*(n + c0)] = h0; s.Huu[c0*BP_RS + hl] = h0;
+                if (2*hg + 1 < m){ s.H[(n + hl) + nm*(n + c1)] = h1; s.Huu[c1*BP_RS + hl] = h1; }
             }
             float a[2*m];
             #pragma unroll
@@ -314,22 +329,33 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
             BP_TRACE(3);
             gauss_jordan_rows<m>(a, t);
             if (t < m){
-                *reinterpret_cast<float4*>(&s.Hinv[t*8]) = make_float4(a[m], a[m+1], a[m+2], a[m+3]);
-                *reinterpret_cast<float4*>(&s.Hinv[t*8 + 4]) = make_float4(a[m+4], a[m+5], a[m+6], 0.f);
+                *reinterpret_cast<float4*>(&s.Hinv[t*BP_RS]) = make_float4(a[m], a[m+1], a[m+2], a[m+3]);
+                *reinterpret_cast<float4*>(&s.Hinv[t*BP_RS + 4]) = make_float4(a[m+4], a[m+5], a[m+6], 0.f);
             }
             BP_TRACE(4);
-        } else if (u < 147){
-            float x[14], y0[14], y1[14];
-            ld14(x, sAB + b_kx*n); ld14(y0, s.AB2 + (2*b_kp)*n); ld14(y1, s.AB2 + (2*b_kp+1)*n);
-            const float q0 = bH[b_kx + nm*(2*b_kp)], q1 = bH[b_kx + nm*(2*b_kp+1)];
-            SCHED_FENCE();
-            float v0 = 0.f, v1 = 0.f;
+        } else if (u < 49){
+            // region 1 (rows ky < n, all columns): tile = 2 rows of AB2 x 3 columns of AB
+            float x0[14], x1[14], x2[14], y0[14], y1[14];
+            const int kx0 = 3*b_kxt, r0 = 2*b_kp;
+            ld14(x0, sAB + kx0*n); ld14(x1, sAB + (kx0+1)*n); ld14(x2, sAB + (kx0+2)*n);
+            ld14(y0, s.AB2 + r0*n); ld14(y1, s.AB2 + (r0+1)*n);
+            float q[6];
             #pragma unroll
-            for (int j = 0; j < n; j++){ v0 = FMA(y0[j], x[j], v0); v1 = FMA(y1[j], x[j], v1); }
-            const float h0 = FMA(1.0f, v0, MUL(1.0f, q0)), h1 = FMA(1.0f, v1, MUL(1.0f, q1));
-            s.H[b_kx + nm*(2*b_kp)] = h0; s.H[b_kx + nm*(2*b_kp+1)] = h1;
-            if (b_kx >= n){ s.Hux[(2*b_kp)*8 + b_kx - n] = h0; s.Hux[(2*b_kp+1)*8 + b_kx - n] = h1; }
-        } else if (u < 196){
+            for (int c = 0; c < 3; c++){ q[c] = bH[kx0 + c + nm*r0]; q[3+c] = bH[kx0 + c + nm*(r0+1)]; }
+            SCHED_FENCE();
+            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            #pragma unroll
+            for (int j = 0; j < n; j++){
+                v[0] = FMA(y0[j], x0[j], v[0]); v[1] = FMA(y0[j], x1[j], v[1]); v[2] = FMA(y0[j], x2[j], v[2]);
+                v[3] = FMA(y1[j], x0[j], v[3]); v[4] = FMA(y1[j], x1[j], v[4]); v[5] = FMA(y1[j], x2[j], v[5]);
+            }
+            #pragma unroll
+            for (int c = 0; c < 3; c++){
+                const float h0 = FMA(1.0f, v[c], MUL(1.0f, q[c])), h1 = FMA(1.0f, v[3+c], MUL(1.0f, q[3+c]));
+                s.H[kx0 + c + nm*r0] = h0; s.H[kx0 + c + nm*(r0+1)] = h1;
+                if (kx0 + c >= n){ s.Hux[r0*BP_RS + kx0 + c - n] = h0; s.Hux[(r0+1)*BP_RS + kx0 + c - n] = h1; }
+            }
+        } else if (u >= 64 && u < 113){
             float y[14], x0[14], x1[14];
             ld14(y, s.AB2 + b2_ky*n); ld14(x0, sAB + (2*b2_kxp)*n); ld14(x1, sAB + (2*b2_kxp+1)*n);
             const float q0 = bH[2*b2_kxp + nm*b2_ky], q1 = bH[2*b2_kxp + 1 + nm*b2_ky];
@@ -338,8 +364,8 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
             #pragma unroll
             for (int j = 0; j < n; j++){ v0 = FMA(y[j], x0[j], v0); v1 = FMA(y[j], x1[j], v1); }
             s.H[2*b2_kxp + nm*b2_ky] = FMA(1.0f, v0, MUL(1.0f, q0)); s.H[2*b2_kxp + 1 + nm*b2_ky] = FMA(1.0f, v1, MUL(1.0f, q1));
-        } else if (u < 196 + nm){
-            const int r = u - 196;
+        } else if (u >= 128 && u < 128 + nm){
+            const int r = u - 128;
             float x[14], y[14];
             ld14(x, s.p); ld14(y, sAB + r*n);
             s.g[r] = FMA(1.0f, dotr<n>(x, y), MUL(1.0f, bg[r]));
@@ -351,12 +377,12 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
         if (PDDP_BP_SKIP & 8){ } else
         if (t < n*m){
             float hi[8], hx[8];
-            ld8(hi, s.Hinv + c_kx*8); ld8(hx, s.Hux + c_ky*8);
-            s.K[c_ky*8 + c_kx] = MUL(1.0f, dotr<m>(hi, hx));
+            ld8(hi, s.Hinv + c_kx*BP_RS); ld8(hx, s.Hux + c_ky*BP_RS);
+            s.K[c_ky*BP_RS + c_kx] = MUL(1.0f, dotr<m>(hi, hx));
         } else if (t >= 128 && t < 128 + m){
             const int r = t - 128;
             float hi[8], gu[8];
-            ld8(hi, s.Hinv + r*8);
+            ld8(hi, s.Hinv + r*BP_RS);
             #pragma unroll
             for (int j = 0; j < m; j++){ gu[j] = s.g[n + j]; }
             gu[7] = 0.f;
@@ -370,15 +396,15 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
         if (t < n*m){
             if (do_ctg){
                 float k[8], h[8];
-                ld8(k, s.K + d_kx*8); ld8(h, s.Huu + d_ky*8);
+                ld8(k, s.K + d_kx*BP_RS); ld8(h, s.Huu + d_ky*BP_RS);
                 const float hxu = s.H[d_kx + nm*(n + d_ky)];
-                s.T[d_kx*8 + d_ky] = SUB(dotr<m>(k, h), hxu);
+                s.T[d_kx*BP_RS + d_ky] = SUB(dotr<m>(k, h), hxu);
             }
         } else if (t >= 196 + n && t < 196 + n + m){
             const int ind = t - (196 + n);
             float h[m];
             #pragma unroll
-            for (int j = 0; j < m; j++){ h[j] = s.Huu[j*8 + ind]; }
+            for (int j = 0; j < m; j++){ h[j] = s.Huu[j*BP_RS + ind]; }
             float dot = 0.f;
             #pragma unroll
             for (int j = 0; j < m; j++){ dot = FMA(h[j], s.du[j], dot); }
@@ -388,25 +414,31 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
         BP_TRACE(7);
         // ---- stage E: cost-to-go of the previous knot (bpHelpers.cuh:242-276)
         if (do_ctg && !(PDDP_BP_SKIP & 32)){
-            if (t >= 32 && t < 32 + n*n){
-                float a[8], c[8], k2[8], h2[8];
-                ld8(a, s.T + e_kx*8); ld8(c, s.K + e_ky*8); ld8(k2, s.K + e_kx*8); ld8(h2, s.Hux + e_ky*8);
-                const float hxx = s.H[e_kx + e_ky*nm];
+            if (t >= 32 && t < 32 + 49){
+                // tile = 2 x 2 entries of P: rows kx0, kx0+1 of T and K, rows ky0, ky0+1 of K and Hux
+                const int kx0 = 2*e_kxp, ky0 = 2*e_kyp;
+                float a0[8], a1[8], kx_0[8], kx_1[8], ky_0[8], ky_1[8], h0[8], h1[8];
+                ld8(a0, s.T + kx0*BP_RS); ld8(a1, s.T + (kx0+1)*BP_RS); ld8(kx_0, s.K + kx0*BP_RS); ld8(kx_1, s.K + (kx0+1)*BP_RS);
+                ld8(ky_0, s.K + ky0*BP_RS); ld8(ky_1, s.K + (ky0+1)*BP_RS); ld8(h0, s.Hux + ky0*BP_RS); ld8(h1, s.Hux + (ky0+1)*BP_RS);
+                const float x00 = s.H[kx0 + ky0*nm], x10 = s.H[kx0 + 1 + ky0*nm], x01 = s.H[kx0 + (ky0+1)*nm], x11 = s.H[kx0 + 1 + (ky0+1)*nm];
                 SCHED_FENCE();
-                float val = 0.f;
+                float v00 = 0.f, v10 = 0.f, v01 = 0.f, v11 = 0.f;            // v(kx, ky)
                 #pragma unroll
-                for (int j = 0; j < m; j++){ val = ADD(val, FMA(a[j], c[j], -MUL(k2[j], h2[j]))); }
-                const float v = ADD(hxx, val);
-#ifdef PDDP_BP_TRACE
-                if (v == 1.2345e-30f){ S.dbg[4000] = 1; }
-                BP_TRACE(10);
-#endif
-                s.P[te] = v; s.Pr[te] = (e_kx == e_ky) ? ADD(v, rho) : v;
-                BP_TRACE(11);
+                for (int j = 0; j < m; j++){
+                    v00 = ADD(v00, FMA(a0[j], ky_0[j], -MUL(kx_0[j], h0[j]))); v10 = ADD(v10, FMA(a1[j], ky_0[j], -MUL(kx_1[j], h0[j])));
+                    v01 = ADD(v01, FMA(a0[j], ky_1[j], -MUL(kx_0[j], h1[j]))); v11 = ADD(v11, FMA(a1[j], ky_1[j], -MUL(kx_1[j], h1[j])));
+                }
+                const float p00 = ADD(x00, v00), p10 = ADD(x10, v10), p01 = ADD(x01, v01), p11 = ADD(x11, v11);
+                *reinterpret_cast<float2*>(&s.P[ky0*n + kx0]) = make_float2(p00, p10);
+                *reinterpret_cast<float2*>(&s.P[(ky0+1)*n + kx0]) = make_float2(p01, p11);
+                // P + rho I: the diagonal entries of this tile are (kx0, ky0) and (kx0+1, ky0+1) when kx0 == ky0
+                const bool dg = (kx0 == ky0);
+                *reinterpret_cast<float2*>(&s.Pr[ky0*n + kx0]) = make_float2(dg ? ADD(p00, rho) : p00, p10);
+                *reinterpret_cast<float2*>(&s.Pr[(ky0+1)*n + kx0]) = make_float2(p01, dg ? ADD(p11, rho) : p11);
             } else if (t >= 228 && t < 228 + n){
                 const int r = t - 228;
                 float a[8], k2[8];
-                ld8(a, s.T + r*8); ld8(k2, s.K + r*8);
+                ld8(a, s.T + r*BP_RS); ld8(k2, s.K + r*BP_RS);
                 float val = 0.f;
                 #pragma unroll
                 for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], a[j], -MUL(k2[j], s.g[n + j]))); }
