@@ -467,38 +467,55 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
 // forward sweep: x_a[k+1] = xp[k+1] + ( -alpha_a Bdu_k + (A-BK)_k (x_a[k]-xp[k]) + [boundary] d_k )
 // grid = B*splits CTAs of 32*A/splits threads; the whole (A-BK) sequence of the problem is staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int SWEEP_CHUNKS = 8;
 template <int n>
 __global__ void sweep_kernel(DevState S, int splits, int b0){
     extern __shared__ __align__(16) float sw[];
+    __shared__ unsigned long long full[SWEEP_CHUNKS];
     // `splits` CTAs share one problem (each takes A/splits step sizes) so that a small batch still covers the SMs
     const int b = b0 + blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
     if (S.done[b]){ return; }
-    float *sA = sw;                         // [N-1][n*n]
-    float *sB = sA + (size_t)(N-1)*n*n;     // [N-1][n]
-    float *sxp = sB + (size_t)(N-1)*n;      // [N][n]
+    float *sA = sw;                         // [N][n*n]   (A - BK), the last entry is never read
+    float *sB = sA + (size_t)N*n*n;         // [N][n]
+    float *sxp = sB + (size_t)N*n;          // [N][n]
     float *sd = sxp + (size_t)N*n;          // [N][n] (only boundary knots are read)
-    {
-        const float4 *src = reinterpret_cast<const float4*>(S.ApBK + (size_t)b*N*n*n); float4 *dst = reinterpret_cast<float4*>(sA);
-        for (int i = threadIdx.x; i < (N-1)*n*n/4; i += blockDim.x){ dst[i] = src[i]; }
-        const float *gB = S.Bdu + (size_t)b*N*n, *gxp = S.xp + (size_t)b*N*n, *gd = S.dp + (size_t)b*N*n;
-        for (int i = threadIdx.x; i < (N-1)*n; i += blockDim.x){ sB[i] = gB[i]; }
-        for (int i = threadIdx.x; i < N*n; i += blockDim.x){ sxp[i] = gxp[i]; sd[i] = gd[i]; }
+    // the problem's whole sequence is staged by TMA bulk copies in SWEEP_CHUNKS slices of N/SWEEP_CHUNKS knots, each with its
+    // own mbarrier: the recursion starts as soon as the first slice has landed and never waits again in practice
+    const int CH = N / SWEEP_CHUNKS;
+    if (threadIdx.x == 0){
+        for (int c = 0; c < SWEEP_CHUNKS; c++){ mbar_init(&full[c], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (threadIdx.x == 0){
+        const float *gA = S.ApBK + (size_t)b*N*n*n, *gB = S.Bdu + (size_t)b*N*n, *gxp = S.xp + (size_t)b*N*n, *gd = S.dp + (size_t)b*N*n;
+        for (int c = 0; c < SWEEP_CHUNKS; c++){
+            const unsigned bytesA = (unsigned)(CH*n*n*4), bytesV = (unsigned)(CH*n*4);
+            mbar_expect_tx(&full[c], bytesA + 3*bytesV);
+            tma_load_1d(sA + (size_t)c*CH*n*n, gA + (size_t)c*CH*n*n, bytesA, &full[c]);
+            tma_load_1d(sB + (size_t)c*CH*n, gB + (size_t)c*CH*n, bytesV, &full[c]);
+            tma_load_1d(sxp + (size_t)c*CH*n, gxp + (size_t)c*CH*n, bytesV, &full[c]);
+            tma_load_1d(sd + (size_t)c*CH*n, gd + (size_t)c*CH*n, bytesV, &full[c]);
+        }
+    }
     const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;
     if (a >= S.A){ return; }
     const float alpha = S.alpha[a];
     float *gx = S.x + ((size_t)b*S.A + a)*N*n;
+    mbar_wait(&full[0], 0);
     float xk = (l < n) ? sxp[l] : 0.f;      // x_a[0] = xp[0]
     if (l < n){ gx[l] = xk; }
+    int to_boundary = NBF, to_chunk = CH;   // steps until k+1 is a shooting-interval boundary / enters the next slice
     for (int k = 0; k < N-1; k++){
+        if (--to_chunk == 0){ to_chunk = CH; mbar_wait(&full[(k+1)/CH], 0); }      // x_p[k+1] lives in the next slice
         const float *Ak = sA + (size_t)k*n*n;
         float dx = (l < n) ? SUB(xk, sxp[k*n + l]) : 0.f;
         float val = 0.f;
         #pragma unroll
         for (int i = 0; i < n; i++){ float dxi = __shfl_sync(FULL, dx, i); if (l < n){ val = FMA(Ak[l + n*i], dxi, val); } }
+        const bool onb = (--to_boundary == 0);
+        if (onb){ to_boundary = NBF; }
         if (l < n){
-            const bool onb = (((k+1) % NBF) == 0) && (k < N-1);
             float tt = ADD(FMA(-alpha, sB[k*n+l], val), onb ? sd[k*n+l] : 0.f);
             xk = ADD(sxp[(k+1)*n + l], tt);
             gx[(k+1)*n + l] = xk;

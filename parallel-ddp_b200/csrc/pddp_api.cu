@@ -121,7 +121,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     CKC(cudaMallocHost((void**)&h->h_nactive, sizeof(int)));
     // dynamic shared memory of each kernel
     h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
-    h->smem_sweep = ((size_t)(N-1)*n*n + (size_t)(N-1)*n + (size_t)2*N*n)*sizeof(float);
+    h->smem_sweep = ((size_t)N*n*n + (size_t)3*N*n)*sizeof(float);
     h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
     h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
