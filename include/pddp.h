@@ -67,7 +67,10 @@ const char *pddp_last_error(pddp_handle h);
  *                                                                   slots are left as NaN / -99
  *   iters_out [batch]                                               iterations used per problem
  *   times_ms[6]: total, sim, sweep, bp, nis, init  -- device time of each phase summed over iterations (CUDA events);
- *                may be NULL.  rollout must be 0, clear must be 1 (warm starts are a "next" row). */
+ *                may be NULL.
+ *   forwardRolloutFlag / clearVarsFlag are loadVarsGPU's (nisInitHelpers.cuh:594-652): clear = 0 starts from the P0, p0,
+ *   KT0, d0 given to pddp_set_warm_start; rollout = 1 first simulates the given trajectory with alpha[0], du = 0 and the
+ *   feedback gains around it, and iterates from the result (alphaOut[0] = 0 instead of -1). */
 int pddp_solve(pddp_handle h, const float *x0, const float *u0, const float *xGoal,
                int forwardRolloutFlag, int clearVarsFlag, int ignoreFirstDefectFlag,
                float *x_out, float *u_out, float *Jout, int *alphaOut, int *iters_out, double *times_ms);
@@ -110,6 +113,14 @@ int pddp_set_groups(pddp_handle h, int groups);
 
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);
+
+/* Warm-start inputs of runiLQR_GPU (its KT0, P0, p0, d0 arguments, DDPWrappers.cuh:8): HOST arrays [batch][N][.] in the
+ * reference layouts -- KT0 14x7 (98 floats per knot), P0 14x14 (196), p0 14, d0 14.  They are kept on the device and used
+ * by every later solve with clearVarsFlag = 0. */
+int pddp_set_warm_start(pddp_handle h, const float *KT0, const float *P0, const float *p0, const float *d0);
+/* loadVarsGPU flags of the NEXT pddp_solve_device call (pddp_solve takes them as arguments); they fall back to
+ * rollout = 0, clear = 1 afterwards. */
+int pddp_set_start_mode(pddp_handle h, int forwardRolloutFlag, int clearVarsFlag);
 
 /* self-test: compares the library's reciprocal (pddp_math.cuh rcp_rn) with the IEEE division 1.0f/x the reference
  * compiles to (e.g. DDPHelpers/invHelpers.cuh pivot reciprocals) on all 2^32 float bit patterns; *mismatches = count. */

@@ -137,6 +137,8 @@ void runiLQR_GPU(T *x0, T *u0, T *KT0, T *P0, T *p0, T *d0, T *xGoal, T *Jout, i
                  T *d_I = nullptr, T *d_Tbody = nullptr){
     pddp_handle h = reinterpret_cast<pddp_handle>(d_x);
     std::vector<float> Jtmp(MAX_ITER+1); std::vector<int> atmp(MAX_ITER+1); int iters = 0; double times[6];
+    // loadVarsGPU reads KT0, P0, p0, d0 only when clearVarsFlag = 0 (nisInitHelpers.cuh:622-631)
+    if (!clearVarsFlag && pddp_set_warm_start(h, KT0, P0, p0, d0) != 0){ pddp_shim_die(h, "pddp_set_warm_start"); }
     if (pddp_solve(h, x0, u0, xGoal, forwardRolloutFlag, clearVarsFlag, ignoreFirstDefectFlag, x0, u0, Jtmp.data(), atmp.data(), &iters, times) != 0){ pddp_shim_die(h, "pddp_solve"); }
     // the reference only writes the slots it used (Jout[0..iters], alphaOut[0..iters])
     for (int i = 0; i <= iters; i++){ Jout[i] = Jtmp[i]; alphaOut[i] = atmp[i]; }

@@ -80,6 +80,9 @@ void  orc_cost_grad(const orc_cfg *c, float *H, float *g, const float *x, const 
 /* phases, operating on a workspace */
 void  orc_load(const orc_cfg *c, orc_ws *w, const float *x0, const float *u0, const float *xg);        /* loadVarsGPU, clear=1, rollout=0 */
 void  orc_init(const orc_cfg *c, orc_ws *w, float *Jout, int *alphaOut);                               /* initAlgGPU */
+void  orc_load_ex(const orc_cfg *c, orc_ws *w, const float *x0, const float *u0, const float *xg,
+                  const float *KT0, const float *P0, const float *p0, const float *d0, int clear, int rollout, int ignore_first); /* loadVarsGPU, all flags */
+void  orc_init_ex(const orc_cfg *c, orc_ws *w, float *Jout, int *alphaOut, int rollout);
 int   orc_backward_pass(const orc_cfg *c, orc_ws *w);                                                   /* backwardPassGPU incl. rho retry */
 void  orc_backward_pass_once(const orc_cfg *c, orc_ws *w, float rho);                                   /* one backPassKern launch */
 void  orc_forward_sweep(const orc_cfg *c, orc_ws *w);                                                   /* forwardSweepKern, all alpha */
@@ -92,6 +95,10 @@ void  orc_next_iteration_setup(const orc_cfg *c, orc_ws *w);                    
 /* whole solve: returns iterations used; x_out/u_out = accepted trajectory (storeVarsGPU) */
 int   orc_solve(const orc_cfg *c, const float *x0, const float *u0, const float *xg,
                 float *x_out, float *u_out, float *Jout /*[max_iter+1]*/, int *alphaOut /*[max_iter+1]*/);
+
+/* same with runiLQR_GPU's warm-start inputs and flags (KT0/P0/p0/d0 may be NULL when clear = 1) */
+int   orc_solve_ex(const orc_cfg *c, const float *x0, const float *u0, const float *xg, const float *KT0, const float *P0, const float *p0, const float *d0,
+                   int rollout, int clear, int ignore_first, float *x_out, float *u_out, float *Jout, int *alphaOut);
 
 int   orc_fma_mode(void); /* the ORACLE_FMA this library was built with */
 

@@ -15,6 +15,7 @@
  * Modes
  *   solve  <G|C|P> <seed0> <nseeds> <tol_cost> <out.bin>
  *   trace  <G|H>   <seed>  <tol_cost> <max_dump_iters> <out.bin>     (H = host math, GPU control flow)
+ *   warm   G       <seed>  <tol_cold> <tol_warm> <out.bin>            (cold solve, then warm starts with (rollout, clear) = (1,0), (0,0), (1,1))
  *   unit   <G|H>   <nsamples> <seed> <out.bin>                       (dynamics / gradient / cost on random x,u)
  *   time   <G|C|P> <seed0> <nseeds> <tol_cost>                       (prints one summary line)
  */
@@ -489,6 +490,56 @@ static int run_unit(char hw, int n, unsigned seed){
 	return 0;
 }
 
+// ---------------------------------------------------------------- warm start (loadVarsGPU's clearVarsFlag = 0 / forwardRolloutFlag = 1, nisInitHelpers.cuh:594-652)
+// solve 1: cold start (tol1).  Its solution, feedback gains, cost-to-go and defects become the warm-start inputs of three
+// second solves (tol2) from a perturbed first knot and a moved goal: (rollout, clear) = (1,0), (0,0), (1,1).
+static int run_warm(unsigned seed, double tol1, double tol2){
+	GpuVars v; gpu_alloc(v);
+	std::vector<T> x0(v.ld_x*NT), u0(v.ld_u*NT);
+	std::vector<T> Jout(MAX_ITER+1, NAN); std::vector<int> alphaOut(MAX_ITER+1, SENT_ALPHA);
+	std::vector<double> simT(MAX_ITER), swT(MAX_ITER), bpT(MAX_ITER), nisT(MAX_ITER); double tTime, initTime;
+	loadXU_seeded(x0.data(), u0.data(), v.xGoal, v.ld_x, v.ld_u, seed);
+	g_tol_cost = tol1;
+	#define RUN_(ROLL, CLEAR, KT0_, P0_, p0_, d0_) runiLQR_GPU<T>(x0.data(), u0.data(), KT0_, P0_, p0_, d0_, v.xGoal, Jout.data(), alphaOut.data(), ROLL, CLEAR, 1, \
+		&tTime, simT.data(), swT.data(), bpT.data(), nisT.data(), &initTime, v.streams, \
+		v.d_x, v.h_d_x, v.d_xp, v.d_xp2, v.d_u, v.h_d_u, v.d_up, v.d_P, v.d_p, v.d_Pp, v.d_pp, v.d_AB, v.d_H, v.d_g, v.d_KT, v.d_du, \
+		v.d_d, v.h_d_d, v.d_dp, v.d_dT, v.d, v.d_ApBK, v.d_Bdu, v.d_dM, v.alpha, v.d_alpha, v.alphaIndex, v.d_JT, v.J, v.dJexp, v.d_dJexp, v.d_xGoal, \
+		v.err, v.d_err, v.ld_x, v.ld_u, v.ld_P, v.ld_p, v.ld_AB, v.ld_H, v.ld_g, v.ld_KT, v.ld_du, v.ld_d, v.ld_A, v.d_I, v.d_Tbody)
+	RUN_(0, 1, nullptr, nullptr, nullptr, nullptr);
+	dumpf("J1", Jout.data(), Jout.size()); dumpi("alpha1", alphaOut.data(), alphaOut.size());
+	std::vector<T> KT0(v.ld_KT*DIM_KT_c*NT), P0(v.ld_P*DIM_P_c*NT), p0(v.ld_p*NT), d0(v.ld_d*NT);
+	gpuErrchk(cudaMemcpy(KT0.data(), v.d_KT, KT0.size()*sizeof(T), cudaMemcpyDeviceToHost));
+	gpuErrchk(cudaMemcpy(P0.data(), v.d_P, P0.size()*sizeof(T), cudaMemcpyDeviceToHost));
+	gpuErrchk(cudaMemcpy(p0.data(), v.d_p, p0.size()*sizeof(T), cudaMemcpyDeviceToHost));
+	gpuErrchk(cudaMemcpy(d0.data(), v.h_d_d[*v.alphaIndex], d0.size()*sizeof(T), cudaMemcpyDeviceToHost));
+	// the reference never writes the last knot of KT / P / p: zero what it left there so that the inputs are well defined
+	for (int i = 0; i < v.ld_KT*DIM_KT_c; i++){KT0[(size_t)v.ld_KT*DIM_KT_c*(NT-1) + i] = 0;}
+	for (int i = 0; i < v.ld_P*DIM_P_c; i++){P0[(size_t)v.ld_P*DIM_P_c*(NT-1) + i] = 0;}
+	for (int i = 0; i < v.ld_p; i++){p0[(size_t)v.ld_p*(NT-1) + i] = 0;}
+	// perturbed start: measured first knot off the plan, goal moved
+	std::vector<T> xs = x0, us = u0;
+	for (int i = 0; i < NUM_POS; i++){xs[i] += static_cast<T>(0.01*(i+1)/NUM_POS); xs[NUM_POS+i] += static_cast<T>(0.02*(NUM_POS-i)/NUM_POS);}
+	v.xGoal[3] += static_cast<T>(0.1); v.xGoal[5] -= static_cast<T>(0.05);
+	dumpf("x_in", xs.data(), xs.size()); dumpf("u_in", us.data(), us.size()); dumpf("xGoal", v.xGoal, STATE_SIZE);
+	dumpf("KT0", KT0.data(), KT0.size()); dumpf("P0", P0.data(), P0.size()); dumpf("p0", p0.data(), p0.size()); dumpf("d0", d0.data(), d0.size());
+	g_tol_cost = tol2;
+	const int flags[3][2] = {{1,0},{0,0},{1,1}};
+	for (int c = 0; c < 3; c++){
+		x0 = xs; u0 = us; std::fill(Jout.begin(), Jout.end(), NAN); std::fill(alphaOut.begin(), alphaOut.end(), SENT_ALPHA);
+		RUN_(flags[c][0], flags[c][1], KT0.data(), P0.data(), p0.data(), d0.data());
+		char nmb[32];
+		snprintf(nmb, sizeof nmb, "Jout_%d%d", flags[c][0], flags[c][1]); dumpf(nmb, Jout.data(), Jout.size());
+		snprintf(nmb, sizeof nmb, "alphaOut_%d%d", flags[c][0], flags[c][1]); dumpi(nmb, alphaOut.data(), alphaOut.size());
+		snprintf(nmb, sizeof nmb, "x_out_%d%d", flags[c][0], flags[c][1]); dumpf(nmb, x0.data(), x0.size());
+		snprintf(nmb, sizeof nmb, "u_out_%d%d", flags[c][0], flags[c][1]); dumpf(nmb, u0.data(), u0.size());
+	}
+	#undef RUN_
+	int meta[4] = {NT, NA, M_BLOCKS, 1}; dumpi("meta", meta, 4); dumpf("alpha", v.alpha, NA);
+	double tols[2] = {tol1, tol2}; dumpd("tols", tols, 2);
+	gpu_free(v);
+	return 0;
+}
+
 int main(int argc, char **argv){
 	if (argc < 2){fprintf(stderr, "usage: see header of ref_driver.cu\n"); return 2;}
 	std::string mode(argv[1]);
@@ -507,6 +558,10 @@ int main(int argc, char **argv){
 	if (mode == "unit" && argc == 6){
 		g_out = fopen(argv[5], "wb"); if (!g_out){perror("open"); return 1;}
 		int rc = run_unit(argv[2][0], atoi(argv[3]), (unsigned)atoi(argv[4])); fclose(g_out); return rc;
+	}
+	if (mode == "warm" && argc == 7 && argv[2][0] == 'G'){
+		g_out = fopen(argv[6], "wb"); if (!g_out){perror("open"); return 1;}
+		int rc = run_warm((unsigned)atoi(argv[3]), atof(argv[4]), atof(argv[5])); fclose(g_out); return rc;
 	}
 	fprintf(stderr, "bad arguments\n"); return 2;
 }

@@ -39,7 +39,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -74,6 +74,8 @@ def load_library():
     L.pddp_last_launch_count.argtypes = [H]; L.pddp_last_launch_count.restype = C.c_long
     L.pddp_set_groups.argtypes = [H, C.c_int]
     L.pddp_selftest_rcp.argtypes = [C.POINTER(C.c_ulonglong)]
+    L.pddp_set_warm_start.argtypes = [H, FP, FP, FP, FP]
+    L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -138,9 +140,20 @@ class Solver:
             raise PddpError(f"{what} failed ({rc}): {self.L.pddp_last_error(self.h).decode()}")
 
     # ---- solver entry point -------------------------------------------------------------------------------------
-    def runiLQR_GPU(self, x0, u0, xGoal, forwardRolloutFlag=0, clearVarsFlag=1, ignoreFirstDefectFlag=1, want_times=False):
-        """Batched runiLQR_GPU.  x0 [B,N,14], u0 [B,N,7], xGoal [B,14] (or [14]).  Returns dict(x, u, Jout, alphaOut, iters[, times_ms])."""
+    def set_warm_start(self, KT0, P0, p0, d0):
+        """runiLQR_GPU's KT0, P0, p0, d0: [B,N,98], [B,N,196], [B,N,14], [B,N,14] in the reference layouts."""
         B, N = self.cfg.batch, self.cfg.N
+        a, pa = _f(np.broadcast_to(KT0, (B, N, 98))); b, pb = _f(np.broadcast_to(P0, (B, N, 196)))
+        c, pc = _f(np.broadcast_to(p0, (B, N, 14))); d, pd = _f(np.broadcast_to(d0, (B, N, 14)))
+        self._ck(self.L.pddp_set_warm_start(self.h, pa, pb, pc, pd), "pddp_set_warm_start")
+
+    def runiLQR_GPU(self, x0, u0, xGoal, forwardRolloutFlag=0, clearVarsFlag=1, ignoreFirstDefectFlag=1, want_times=False,
+                    KT0=None, P0=None, p0=None, d0=None):
+        """Batched runiLQR_GPU.  x0 [B,N,14], u0 [B,N,7], xGoal [B,14] (or [14]).  Returns dict(x, u, Jout, alphaOut, iters[, times_ms]).
+        KT0, P0, p0, d0 (reference argument order: x0, u0, KT0, P0, p0, d0) are used when clearVarsFlag = 0."""
+        B, N = self.cfg.batch, self.cfg.N
+        if KT0 is not None:
+            self.set_warm_start(KT0, P0, p0, d0)
         x0, px = _f(np.broadcast_to(x0, (B, N, 14))); u0, pu = _f(np.broadcast_to(u0, (B, N, 7))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
         L1 = self.cfg.max_iter + 1
         x = np.empty((B, N, 14), np.float32); u = np.empty((B, N, 7), np.float32)

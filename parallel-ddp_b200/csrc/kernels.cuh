@@ -45,6 +45,7 @@ struct DevState {
     int *iter, *alphaIndex, *ignore_defect, *done, *accepted, *final_src;
     float *Jout; int *alphaOut;    // [B][max_iter+1]
     int *n_active;                 // [1]
+    int rolled_out;                // this solve started with loadVarsGPU's forward rollout
     long long *dbg;                // [4096] stage clocks of CTA 0 (only written by -DPDDP_BP_TRACE builds)
 };
 
@@ -551,14 +552,14 @@ __device__ __forceinline__ float cost_knot(const float *x, const float *u, const
     return MUL(0.5f, cost);
 }
 
-__global__ void sim_kernel(DevState S, int b0){
+__global__ void sim_kernel(DevState S, int b0, int n_cand){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES, GPW = 32 / SIM_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw);            // 252
     float *sTb = sI + 36*kuka::NB;                             // 252
     float *sxg = sTb + 36*kuka::NB;                            // 16
     SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sxg + 16);
-    const int apb = (S.A + GPW - 1) / GPW;                     // CTAs per problem
+    const int apb = (n_cand + GPW - 1) / GPW;                  // CTAs per problem (n_cand = A, or 1 for the initial rollout)
     const int b = b0 + blockIdx.x / apb;
     if (S.done[b]){ return; }
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
@@ -567,8 +568,8 @@ __global__ void sim_kernel(DevState S, int b0){
     const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
     if (w >= S.M){ return; }
     int a = (blockIdx.x % apb)*GPW + grp;
-    const bool live = a < S.A;                                 // odd A: the last half-warp replays candidate A-1 without storing
-    if (!live){ a = S.A - 1; }
+    const bool live = a < n_cand;                              // odd count: the last half-warp replays the last candidate without storing
+    if (!live){ a = n_cand - 1; }
     SimGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
@@ -680,7 +681,7 @@ __global__ void select_kernel(DevState S, int mode, int b0){
     float *Jout = S.Jout + (size_t)b*(S.max_iter+1); int *alphaOut = S.alphaOut + (size_t)b*(S.max_iter+1);
     if (mode == 1){
         float pj = ADD(sJ[0], S.two_tol);                  // nisInitHelpers.cuh:393
-        S.prevJ[b] = pj; Jout[0] = SUB(pj, S.two_tol); alphaOut[0] = -1;
+        S.prevJ[b] = pj; Jout[0] = SUB(pj, S.two_tol); alphaOut[0] = S.rolled_out ? 0 : -1;     // nisInitHelpers.cuh:363
         return;
     }
     for (int i = 0; i < A; i++){ S.J[(size_t)b*A + i] = sJ[i]; S.dT[(size_t)b*A + i] = sdT[i]; }
@@ -719,7 +720,8 @@ __global__ void select_kernel(DevState S, int mode, int b0){
 // ------------------------------------------------------------------------------------------------------------------
 // next-iteration setup: one warp per (problem, knot).  Hands the accepted candidate over to (xp,up,dp), keeps the
 // previous one in xp2, and refreshes AB (analytic Euler gradient), g (and H when write_H) at the accepted trajectory.
-// mode 1 = initialisation: the trajectory is already in xp/up, xp2 <- xp.
+// mode 1 = initialisation: the trajectory is already in xp/up, xp2 <- xp.  mode 2 = initialisation after the forward
+// rollout of loadVarsGPU: candidate 0 is handed over first and becomes xp, xp2, up, dp.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int NIS_LANES = 32;
 struct NisGroupSmem {
@@ -753,12 +755,13 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     NisGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
-    const bool acc = (mode == 0) && S.accepted[b];
+    const bool acc = (mode == 2) || ((mode == 0) && S.accepted[b]);      // mode 2: initialisation after a forward rollout
     const int a = S.alphaIndex[b];
     const float *cx = S.x + (((size_t)b*S.A + a)*N + k)*n, *cu = S.u + (((size_t)b*S.A + a)*N + k)*m, *cd = S.d + (((size_t)b*S.A + a)*N + k)*n;
     if (l < n){
-        const float xold = gxp[l]; gxp2[l] = xold;                 // xp2 <- xp (fpHelpers.cuh:371 / nisInitHelpers.cuh:379)
+        const float xold = gxp[l];
         const float xv = acc ? cx[l] : xold; s.x[l] = xv;
+        gxp2[l] = (mode == 2) ? xv : xold;                         // xp2 <- xp (fpHelpers.cuh:371); initAlgGPU sets both to the start trajectory (nisInitHelpers.cuh:378-379)
         if (acc){ gxp[l] = xv; gdp[l] = cd[l]; }
     }
     if (l < m){ const float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }

@@ -27,6 +27,8 @@ struct pddp_solver {
     std::vector<void*> allocs;
     std::string err;
     int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
+    float *w_KT = nullptr, *w_P = nullptr, *w_p = nullptr, *w_d = nullptr;     // warm-start inputs (pddp_set_warm_start)
+    int next_clear = 1, next_rollout = 0;                                      // loadVarsGPU flags of the next solve
     long launches = 0;
     int n, m, num_sms = 148;
     float *d_xout = nullptr, *d_uout = nullptr; int *d_iters = nullptr;
@@ -163,22 +165,42 @@ __global__ void reset_kernel(DevState S, float rho_init, int ignore_first){
     }
 }
 
-static int launch_reset(pddp_handle h, int ignore_first){
+static int launch_reset(pddp_handle h, int ignore_first, int clear){
     DevState &S = h->S; const int B = S.B, N = S.N, A = S.A, n = S.n, m = S.m;
-    // loadVarsGPU with clearVarsFlag=1 (nisInitHelpers.cuh:612-634)
-    CK(cudaMemsetAsync(S.Pbuf[0], 0, (size_t)B*N*n*n*4, h->stream)); CK(cudaMemsetAsync(S.Pbuf[1], 0, (size_t)B*N*n*n*4, h->stream));
-    CK(cudaMemsetAsync(S.pbuf[0], 0, (size_t)B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.pbuf[1], 0, (size_t)B*N*n*4, h->stream));
-    CK(cudaMemsetAsync(S.KT, 0, (size_t)B*N*n*m*4, h->stream)); CK(cudaMemsetAsync(S.du, 0, (size_t)B*N*m*4, h->stream));
-    CK(cudaMemsetAsync(S.d, 0, (size_t)B*A*N*n*4, h->stream)); CK(cudaMemsetAsync(S.dp, 0, (size_t)B*N*n*4, h->stream));
+    if (clear){
+        // loadVarsGPU with clearVarsFlag=1 (nisInitHelpers.cuh:612-620)
+        CK(cudaMemsetAsync(S.Pbuf[0], 0, (size_t)B*N*n*n*4, h->stream)); CK(cudaMemsetAsync(S.Pbuf[1], 0, (size_t)B*N*n*n*4, h->stream));
+        CK(cudaMemsetAsync(S.pbuf[0], 0, (size_t)B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.pbuf[1], 0, (size_t)B*N*n*4, h->stream));
+        CK(cudaMemsetAsync(S.KT, 0, (size_t)B*N*n*m*4, h->stream));
+        CK(cudaMemsetAsync(S.d, 0, (size_t)B*A*N*n*4, h->stream)); CK(cudaMemsetAsync(S.dp, 0, (size_t)B*N*n*4, h->stream));
+    } else {
+        // clearVarsFlag=0 (:622-631): P, Pp <- P0; p, pp <- p0; KT <- KT0; d <- d0 (every candidate is based on dp here)
+        if (!h->w_KT){ h->err = "clearVarsFlag=0 needs pddp_set_warm_start first"; return PDDP_E_INVALID; }
+        CK(cudaMemcpyAsync(S.Pbuf[0], h->w_P, (size_t)B*N*n*n*4, cudaMemcpyDeviceToDevice, h->stream)); CK(cudaMemcpyAsync(S.Pbuf[1], h->w_P, (size_t)B*N*n*n*4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(S.pbuf[0], h->w_p, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream)); CK(cudaMemcpyAsync(S.pbuf[1], h->w_p, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(S.KT, h->w_KT, (size_t)B*N*n*m*4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(S.dp, h->w_d, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpy2DAsync(S.d, (size_t)A*N*n*4, h->w_d, (size_t)N*n*4, (size_t)N*n*4, B, cudaMemcpyDeviceToDevice, h->stream));     // candidate 0
+    }
+    // always cleared (:633-637)
+    CK(cudaMemsetAsync(S.du, 0, (size_t)B*N*m*4, h->stream));
     CK(cudaMemsetAsync(S.dT, 0, (size_t)B*A*4, h->stream));
     reset_kernel<<<B, 128, 0, h->stream>>>(S, h->cfg.rho_init, ignore_first);
     h->cur = 0; h->launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
-static int launch_init(pddp_handle h){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
-    DevState &S = h->S;
-    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, 1, 1, 0, S.B);
+static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
+    DevState &S = h->S; const int B = S.B, N = S.N, A = S.A, n = S.n;
+    S.rolled_out = rollout ? 1 : 0;
+    if (rollout){
+        // loadVarsGPU's forward rollout (nisInitHelpers.cuh:646-651): candidate 0 starts as the given trajectory and is simulated
+        // with alpha[0], du = 0 and the feedback gains KT around it; the result (x, u, defects) becomes the start trajectory
+        CK(cudaMemcpy2DAsync(S.x, (size_t)A*N*n*4, S.xp, (size_t)N*n*4, (size_t)N*n*4, B, cudaMemcpyDeviceToDevice, h->stream));
+        sim_kernel<<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1);
+        h->launches += 1;
+    }
+    nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, rollout ? 2 : 1, 1, 0, S.B);
     init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S);
     select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1, 0);
     h->launches += 3;
@@ -200,7 +222,7 @@ static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
 }
 static int launch_sim(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    sim_kernel<<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0);
+    sim_kernel<<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
@@ -267,11 +289,12 @@ extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *
     CK(cudaSetDevice(h->cfg.device));
     h->launches = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
-    if ((rc = launch_reset(h, ignoreFirstDefectFlag))){ return rc; }
+    if ((rc = launch_reset(h, ignoreFirstDefectFlag, h->next_clear))){ return rc; }
     CK(cudaMemcpyAsync(S.xp, d_x0, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(S.up, d_u0, (size_t)B*N*m*4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(S.xGoal, d_xGoal, (size_t)B*n*4, cudaMemcpyDeviceToDevice, h->stream));
-    if ((rc = launch_init(h))){ return rc; }
+    if ((rc = launch_init(h, h->next_rollout))){ return rc; }
+    h->next_clear = 1; h->next_rollout = 0;          // the flags apply to one solve
     CK(cudaEventRecord(h->ev[1], h->stream));
     if ((rc = run_iterations(h, times_ms, h->groups))){ return rc; }
     CK(cudaEventRecord(h->ev[2], h->stream));
@@ -292,7 +315,7 @@ extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *
 extern "C" int pddp_solve(pddp_handle h, const float *x0, const float *u0, const float *xGoal, int forwardRolloutFlag, int clearVarsFlag,
                           int ignoreFirstDefectFlag, float *x_out, float *u_out, float *Jout, int *alphaOut, int *iters_out, double *times_ms){
     if (!h){ return PDDP_E_INVALID; }
-    if (forwardRolloutFlag != 0 || clearVarsFlag != 1){ h->err = "rollout / warm-start modes are not built yet (forwardRolloutFlag=0, clearVarsFlag=1 only)"; return PDDP_E_INVALID; }
+    h->next_clear = clearVarsFlag ? 1 : 0; h->next_rollout = forwardRolloutFlag ? 1 : 0;
     if (!x0 || !u0 || !xGoal){ h->err = "null input"; return PDDP_E_INVALID; }
     DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m, L = S.max_iter + 1; int rc;
     CK(cudaSetDevice(h->cfg.device));
@@ -328,6 +351,29 @@ __global__ void selftest_rcp_kernel(unsigned long long *bad){
     }
     if (local){ atomicAdd(bad, local); }
 }
+}
+extern "C" int pddp_set_warm_start(pddp_handle h, const float *KT0, const float *P0, const float *p0, const float *d0){
+    if (!h){ return PDDP_E_INVALID; }
+    if (!KT0 || !P0 || !p0 || !d0){ h->err = "null warm-start array"; return PDDP_E_INVALID; }
+    DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->w_KT){
+        void *p = nullptr;
+        CK(cudaMalloc(&p, B*N*n*m*4)); h->w_KT = (float*)p; h->allocs.push_back(p);
+        CK(cudaMalloc(&p, B*N*n*n*4)); h->w_P = (float*)p; h->allocs.push_back(p);
+        CK(cudaMalloc(&p, B*N*n*4)); h->w_p = (float*)p; h->allocs.push_back(p);
+        CK(cudaMalloc(&p, B*N*n*4)); h->w_d = (float*)p; h->allocs.push_back(p);
+    }
+    CK(cudaMemcpyAsync(h->w_KT, KT0, B*N*n*m*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->w_P, P0, B*N*n*n*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->w_p, p0, B*N*n*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->w_d, d0, B*N*n*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+extern "C" int pddp_set_start_mode(pddp_handle h, int forwardRolloutFlag, int clearVarsFlag){
+    if (!h){ return PDDP_E_INVALID; }
+    h->next_rollout = forwardRolloutFlag ? 1 : 0; h->next_clear = clearVarsFlag ? 1 : 0; return 0;
 }
 extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
     if (!mismatches){ return PDDP_E_INVALID; }
@@ -448,11 +494,12 @@ extern "C" int pddp_phase_load_init(pddp_handle h, const float *x0, const float 
     if (!h){ return PDDP_E_INVALID; }
     DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m;
     return timed_phase(h, [&](){
-        int rc = launch_reset(h, ignoreFirstDefectFlag); if (rc){ return rc; }
+        const int clear = h->next_clear, rollout = h->next_rollout; h->next_clear = 1; h->next_rollout = 0;
+        int rc = launch_reset(h, ignoreFirstDefectFlag, clear); if (rc){ return rc; }
         CK(cudaMemcpyAsync(S.xp, x0, B*N*n*4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(S.up, u0, B*N*m*4, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(S.xGoal, xGoal, B*n*4, cudaMemcpyHostToDevice, h->stream));
-        return launch_init(h);
+        return launch_init(h, rollout);
     });
 }
 extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ h->cur ^= 1; return launch_bp(h, h->stream, 0, h->S.B); }); }

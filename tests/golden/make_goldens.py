@@ -3,7 +3,7 @@
 built by `make -C oracle ref` from /root/reference -- see oracle/Makefile).
 
   python tests/golden/make_goldens.py host      # here (no GPU): reference HOST instantiation  -> *_H_*.npz
-  python tests/golden/make_goldens.py gpu       # on the GPU box (under gpurun): raw dumps       -> gpurun_out/golden_raw/*.bin
+  python tests/golden/make_goldens.py gpu [prefix]  # on the GPU box (under gpurun): raw dumps   -> gpurun_out/golden_raw/*.bin
   python tests/golden/make_goldens.py import    # here: gpurun_out/golden_raw/*.bin             -> *_G_*.npz
 
 Fixtures are compressed .npz files holding the named arrays ref_driver wrote; redundant broadcast copies
@@ -47,7 +47,10 @@ def jobs(hw):
     if hw == "G":
         out += [(128, ("solve", "G", 0, 64, 0.0), "solve_G_N128_s0-63_tol0"),
                 (128, ("solve", "G", 0, 64, 0.0001), "solve_G_N128_s0-63_tol1e-4"),
-                (32, ("solve", "G", 0, 16, 0.0), "solve_G_N32_s0-15_tol0")]
+                (32, ("solve", "G", 0, 16, 0.0), "solve_G_N32_s0-15_tol0"),
+                # warm starts of loadVarsGPU: cold solve (tol 1e-4), then (rollout, clear) = (1,0), (0,0), (1,1) from a perturbed start
+                (32, ("warm", "G", 1, 0.0001, 0.0), "warm_G_N32_s1"),
+                (128, ("warm", "G", 2, 0.0001, 0.0001), "warm_G_N128_s2")]
     return out
 
 
@@ -63,7 +66,10 @@ def main():
         np.savez(os.path.join(HERE, "kuka_model.npz"), I=d["I"], Tbody=d["Tbody"])
     elif mode == "gpu":
         os.makedirs(RAW, exist_ok=True)
+        only = sys.argv[2] if len(sys.argv) > 2 else ""
         for N, args, name in jobs("G"):
+            if only and not name.startswith(only):
+                continue
             run(N, *args, os.path.join(RAW, name + ".bin"))
     elif mode == "import":
         for f in sorted(os.listdir(RAW)):

@@ -76,6 +76,7 @@ def lib(fma=False):
         getattr(L, fn).argtypes = [cp, wp]
     L.orc_accept_reject.argtypes = [cp, wp, FP, IP]; L.orc_accept_reject.restype = C.c_int
     L.orc_solve.argtypes = [cp, FP, FP, FP, FP, FP, FP, IP]; L.orc_solve.restype = C.c_int
+    L.orc_solve_ex.argtypes = [cp, FP, FP, FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, IP]; L.orc_solve_ex.restype = C.c_int
     L.orc_fma_mode.restype = C.c_int
     assert L.orc_fma_mode() == (1 if fma else 0)
     _libs[name] = L
