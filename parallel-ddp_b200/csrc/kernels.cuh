@@ -578,8 +578,12 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
     float *gx = S.x + ((size_t)b*S.A + a)*N*n, *gu = S.u + ((size_t)b*S.A + a)*N*m, *gdd = S.d + ((size_t)b*S.A + a)*N*n;
     float *gc = S.costk + ((size_t)b*S.A + a)*N;
     const float *gxp = S.xp + (size_t)b*N*n, *gup = S.up + (size_t)b*N*m, *gKT = S.KT + (size_t)b*N*n*m, *gdu = S.du + (size_t)b*N*m;
-    // state at the start of the interval (left there by the sweep)
-    if (l < n){ s.x[l] = gx[kStart*n + l]; }
+    // state at the start of the interval: left there by the sweep; the first interval always starts at xp[0] (with a single
+    // interval there is no sweep at all, fpHelpers.cuh:17-63 is skipped for M_BLOCKS_F = 1)
+    if (l < n){
+        if (w == 0){ const float v = gxp[l]; s.x[l] = v; if (live){ gx[l] = v; } }
+        else { s.x[l] = gx[kStart*n + l]; }
+    }
     // prefetch registers for knot kStart
     constexpr int KTQ = (n*m + LANES - 1) / LANES;
     float rKT[KTQ], rdu = 0.f, rxp = 0.f, rup = 0.f;
