@@ -468,58 +468,73 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int cur, int 
 // forward sweep: x_a[k+1] = xp[k+1] + ( -alpha_a Bdu_k + (A-BK)_k (x_a[k]-xp[k]) + [boundary] d_k )
 // grid = B*splits CTAs of 32*A/splits threads; the whole (A-BK) sequence of the problem is staged in shared memory once.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int SWEEP_CHUNKS = 8;
+constexpr int SWEEP_CH = 16;         // knots per slice
+constexpr int SWEEP_SLOTS = 4;       // slices resident in shared memory
+template <int n>
+struct __align__(16) SweepSlot { float A[SWEEP_CH*n*n], B[SWEEP_CH*n], xp[SWEEP_CH*n], d[SWEEP_CH*n]; };
 template <int n>
 __global__ void sweep_kernel(DevState S, int splits, int b0){
-    extern __shared__ __align__(16) float sw[];
-    __shared__ unsigned long long full[SWEEP_CHUNKS];
+    extern __shared__ __align__(16) unsigned char sw_raw[];
+    __shared__ unsigned long long full[SWEEP_SLOTS];
+    SweepSlot<n> *slots = reinterpret_cast<SweepSlot<n>*>(sw_raw);
     // `splits` CTAs share one problem (each takes A/splits step sizes) so that a small batch still covers the SMs
     const int b = b0 + blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
     if (S.done[b]){ return; }
-    float *sA = sw;                         // [N][n*n]   (A - BK), the last entry is never read
-    float *sB = sA + (size_t)N*n*n;         // [N][n]
-    float *sxp = sB + (size_t)N*n;          // [N][n]
-    float *sd = sxp + (size_t)N*n;          // [N][n] (only boundary knots are read)
-    // the problem's whole sequence is staged by TMA bulk copies in SWEEP_CHUNKS slices of N/SWEEP_CHUNKS knots, each with its
-    // own mbarrier: the recursion starts as soon as the first slice has landed and never waits again in practice
-    const int CH = N / SWEEP_CHUNKS;
+    // The problem's sequence ((A - BK), B du, xp, d per knot) streams through a ring of SWEEP_SLOTS slices of SWEEP_CH knots,
+    // each filled by four TMA bulk copies on its own mbarrier.  The recursion starts as soon as the first slice has landed; a
+    // slice is refilled (CTA barrier, then one thread issues) once every warp has moved two slices past it, so any horizon
+    // N <= 1024 fits in 60 KB of shared memory.
+    const int nslices = N / SWEEP_CH;
+    const float *gA = S.ApBK + (size_t)b*N*n*n, *gB = S.Bdu + (size_t)b*N*n, *gxp = S.xp + (size_t)b*N*n, *gd = S.dp + (size_t)b*N*n;
+    auto issue = [&](int c){
+        SweepSlot<n> &sl = slots[c % SWEEP_SLOTS]; unsigned long long *bar = &full[c % SWEEP_SLOTS];
+        constexpr unsigned bytesA = SWEEP_CH*n*n*4, bytesV = SWEEP_CH*n*4;
+        mbar_expect_tx(bar, bytesA + 3*bytesV);
+        tma_load_1d(sl.A, gA + (size_t)c*SWEEP_CH*n*n, bytesA, bar);
+        tma_load_1d(sl.B, gB + (size_t)c*SWEEP_CH*n, bytesV, bar);
+        tma_load_1d(sl.xp, gxp + (size_t)c*SWEEP_CH*n, bytesV, bar);
+        tma_load_1d(sl.d, gd + (size_t)c*SWEEP_CH*n, bytesV, bar);
+    };
     if (threadIdx.x == 0){
-        for (int c = 0; c < SWEEP_CHUNKS; c++){ mbar_init(&full[c], 1); }
+        for (int c = 0; c < SWEEP_SLOTS; c++){ mbar_init(&full[c], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int c = 0; c < SWEEP_SLOTS && c < nslices; c++){ issue(c); }
     }
     __syncthreads();
-    if (threadIdx.x == 0){
-        const float *gA = S.ApBK + (size_t)b*N*n*n, *gB = S.Bdu + (size_t)b*N*n, *gxp = S.xp + (size_t)b*N*n, *gd = S.dp + (size_t)b*N*n;
-        for (int c = 0; c < SWEEP_CHUNKS; c++){
-            const unsigned bytesA = (unsigned)(CH*n*n*4), bytesV = (unsigned)(CH*n*4);
-            mbar_expect_tx(&full[c], bytesA + 3*bytesV);
-            tma_load_1d(sA + (size_t)c*CH*n*n, gA + (size_t)c*CH*n*n, bytesA, &full[c]);
-            tma_load_1d(sB + (size_t)c*CH*n, gB + (size_t)c*CH*n, bytesV, &full[c]);
-            tma_load_1d(sxp + (size_t)c*CH*n, gxp + (size_t)c*CH*n, bytesV, &full[c]);
-            tma_load_1d(sd + (size_t)c*CH*n, gd + (size_t)c*CH*n, bytesV, &full[c]);
-        }
-    }
-    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;
-    if (a >= S.A){ return; }
+    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;       // blockDim = 32 * (A / splits): every warp has a step size
     const float alpha = S.alpha[a];
     float *gx = S.x + ((size_t)b*S.A + a)*N*n;
     mbar_wait(&full[0], 0);
-    float xk = (l < n) ? sxp[l] : 0.f;      // x_a[0] = xp[0]
+    float xk = (l < n) ? slots[0].xp[l] : 0.f;      // x_a[0] = xp[0]
     if (l < n){ gx[l] = xk; }
-    int to_boundary = NBF, to_chunk = CH;   // steps until k+1 is a shooting-interval boundary / enters the next slice
-    for (int k = 0; k < N-1; k++){
-        if (--to_chunk == 0){ to_chunk = CH; mbar_wait(&full[(k+1)/CH], 0); }      // x_p[k+1] lives in the next slice
-        const float *Ak = sA + (size_t)k*n*n;
-        float dx = (l < n) ? SUB(xk, sxp[k*n + l]) : 0.f;
-        float val = 0.f;
-        #pragma unroll
-        for (int i = 0; i < n; i++){ float dxi = __shfl_sync(FULL, dx, i); if (l < n){ val = FMA(Ak[l + n*i], dxi, val); } }
-        const bool onb = (--to_boundary == 0);
-        if (onb){ to_boundary = NBF; }
-        if (l < n){
-            float tt = ADD(FMA(-alpha, sB[k*n+l], val), onb ? sd[k*n+l] : 0.f);
-            xk = ADD(sxp[(k+1)*n + l], tt);
-            gx[(k+1)*n + l] = xk;
+    int to_boundary = NBF;                   // steps until k+1 is a shooting-interval boundary
+    for (int c = 0; c < nslices; c++){
+        const SweepSlot<n> &sl = slots[c % SWEEP_SLOTS];
+        const bool last = (c == nslices - 1);
+        // slice c-2 is behind every warp of the CTA once all of them are here: hand its slot to slice c-2+SWEEP_SLOTS
+        if (c >= 2 && c - 2 + SWEEP_SLOTS < nslices){
+            __syncthreads();
+            if (threadIdx.x == 0){ issue(c - 2 + SWEEP_SLOTS); }
+        }
+        const int kend = last ? SWEEP_CH - 1 : SWEEP_CH;
+        for (int kk = 0; kk < kend; kk++){
+            const int k = c*SWEEP_CH + kk;
+            // x_p[k+1] of the last knot of a slice lives in the next slice
+            const float *xpn;
+            if (kk == SWEEP_CH - 1){ mbar_wait(&full[(c+1) % SWEEP_SLOTS], ((c+1) / SWEEP_SLOTS) & 1); xpn = slots[(c+1) % SWEEP_SLOTS].xp; }
+            else { xpn = sl.xp + (kk+1)*n; }
+            const float *Ak = sl.A + kk*n*n;
+            float dx = (l < n) ? SUB(xk, sl.xp[kk*n + l]) : 0.f;
+            float val = 0.f;
+            #pragma unroll
+            for (int i = 0; i < n; i++){ float dxi = __shfl_sync(FULL, dx, i); if (l < n){ val = FMA(Ak[l + n*i], dxi, val); } }
+            const bool onb = (--to_boundary == 0);
+            if (onb){ to_boundary = NBF; }
+            if (l < n){
+                float tt = ADD(FMA(-alpha, sl.B[kk*n+l], val), onb ? sl.d[kk*n+l] : 0.f);
+                xk = ADD(xpn[l], tt);
+                gx[(k+1)*n + l] = xk;
+            }
         }
     }
 }

@@ -123,13 +123,12 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     CKC(cudaMallocHost((void**)&h->h_nactive, sizeof(int)));
     // dynamic shared memory of each kernel
     h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
-    h->smem_sweep = ((size_t)N*n*n + (size_t)3*N*n)*sizeof(float);
+    h->smem_sweep = SWEEP_SLOTS*sizeof(SweepSlot<kuka::NX>);
     h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
     h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
     h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
-    if (h->smem_sweep > 227*1024){ h->err = "N too large for the single-pass sweep staging"; return bail(PDDP_E_INVALID); }
     CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
     CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
     CKC(cudaFuncSetAttribute(sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
