@@ -107,7 +107,7 @@ int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
 
 /* Number of independent problem groups, each iterated on its own CUDA stream so that one group's latency-bound kernels
  * (backward pass, sweep, selection) overlap another group's throughput-bound ones (sim, next-iteration setup).  Results do
- * not depend on it.  Default 1 (env PDDP_GROUPS); the per-phase entries of times_ms are only filled with 1 group.
+ * not depend on it.  Default 4 (env PDDP_GROUPS); the per-phase entries of times_ms are only filled with 1 group.
  * Returns the value in effect. */
 int pddp_set_groups(pddp_handle h, int groups);
 

@@ -86,7 +86,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     h->gstreams.push_back(h->stream);
     for (int g = 1; g < 8; g++){ cudaStream_t st; CKC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); h->gstreams.push_back(st); }
     for (int g = 0; g < 9; g++){ cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->gev.push_back(e); }
-    { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 1; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
+    { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 4; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S));
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
     S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter;
