@@ -46,6 +46,7 @@ typedef struct pddp_config {
     float max_defect;                                  /* MAX_DEFECT_SIZE (config.cuh:123-126) */
     float tol_cost;                                    /* TOL_COST (config.cuh:85-87) */
     float Q1, Q2, R, QF1, QF2;                         /* plants/cost_arm.cuh:96-103 */
+    float gravity;                                     /* GRAVITY (dynamics_arm.cuh:42-46): 9.81, or 0 for the reference's MPC_MODE builds */
 } pddp_config;
 
 typedef struct pddp_solver *pddp_handle;
@@ -121,6 +122,25 @@ int pddp_set_warm_start(pddp_handle h, const float *KT0, const float *P0, const 
 /* loadVarsGPU flags of the NEXT pddp_solve_device call (pddp_solve takes them as arguments); they fall back to
  * rollout = 0, clear = 1 afterwards. */
 int pddp_set_start_mode(pddp_handle h, int forwardRolloutFlag, int clearVarsFlag);
+
+/* ---- receding horizon: runiLQR_MPC_GPU (DDPHelpers/MPCHelpers.cuh:862-1045) for `batch` independent arms.
+ * The solver keeps what the reference keeps on the device between solves (current plan and its defects, gains, both cost-to-go
+ * buffers, the per-problem last_successful_solve counter).  The wall-clock budget of the reference (USE_MAX_SOLVER_TIME) is not
+ * reproduced: max_iter is the limit.  Build the config with gravity = 0 to match the reference's MPC_MODE (dynamics_arm.cuh:42-43).
+ *
+ * pddp_mpc_init: x_init [batch][N][14], u_init [batch][N][7] (HOST) -- the plan the first step starts from (trajVars x,u and the
+ *                current candidate slot of the reference); gains, cost-to-go and defects start at zero.
+ * pddp_mpc_step: xActual [batch][14] measured state, xGoal [batch][14], shiftAmount [batch] = whole knots elapsed since the previous
+ *                step (the reference derives it from its plant clock, MPCHelpers.cuh:875), max_iter <= config max_iter,
+ *                clear_vars / ignoreFirstDefectFlag as in the reference.  Does loadVarsGPU_MPC (shift, zero-order hold, open-loop
+ *                rollout from xActual over the whole horizon: FULL_ROLLOUT 1), initAlgGPU, the iteration loop and storeVarsGPU_MPC.
+ *                x, u, KT (HOST, [batch][N][14|7|98]) play trajVars: they are overwritten only for the problems whose solve took a
+ *                step (last_successful_solve == 1 afterwards); otherwise the device state falls back to the shifted previous plan.
+ *                Jout / alphaOut [batch][config max_iter + 1], iters_out, last_successful_solve [batch] may be NULL. */
+int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_init);
+int pddp_mpc_step(pddp_handle h, const float *xActual, const float *xGoal, const int *shiftAmount, int max_iter, int clear_vars,
+                  int ignoreFirstDefectFlag, float *x, float *u, float *KT, float *Jout, int *alphaOut, int *iters_out,
+                  int *last_successful_solve);
 
 /* self-test: compares the library's reciprocal (pddp_math.cuh rcp_rn) with the IEEE division 1.0f/x the reference
  * compiles to (e.g. DDPHelpers/invHelpers.cuh pivot reciprocals) on all 2^32 float bit patterns; *mismatches = count. */

@@ -44,6 +44,7 @@ typedef struct {
     float exp_red_min, exp_red_max, max_defect, tol_cost;
     float Q1, Q2, R, QF1, QF2;   /* cost_arm.cuh:96-103 weights (other plants map theirs here) */
     float I[252], Tbody[252];    /* Kuka spatial inertias / fixed joint transforms (dynamics_arm.cuh:71-427) */
+    float gravity;               /* GRAVITY dynamics_arm.cuh:42-46 (9.81; 0 under MPC_MODE) */
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */
@@ -99,6 +100,15 @@ int   orc_solve(const orc_cfg *c, const float *x0, const float *u0, const float 
 /* same with runiLQR_GPU's warm-start inputs and flags (KT0/P0/p0/d0 may be NULL when clear = 1) */
 int   orc_solve_ex(const orc_cfg *c, const float *x0, const float *u0, const float *xg, const float *KT0, const float *P0, const float *p0, const float *d0,
                    int rollout, int clear, int ignore_first, float *x_out, float *u_out, float *Jout, int *alphaOut);
+
+/* receding horizon (runiLQR_MPC_GPU, MPCHelpers.cuh:862-1045, without its wall-clock budget): persistent state in orc_mpc */
+typedef struct orc_mpc_s orc_mpc;
+orc_mpc *orc_mpc_alloc(const orc_cfg *c, const float *x_init, const float *u_init, const float *xg);
+void  orc_mpc_free(orc_mpc *mp);
+int   orc_mpc_step(const orc_cfg *c, orc_mpc *mp, const float *xActual, const float *xg, int shift, int max_iter, int clear_vars, int ignore_first,
+                   float *Jout, int *alphaOut);
+const float *orc_mpc_x(const orc_mpc *mp); const float *orc_mpc_u(const orc_mpc *mp); const float *orc_mpc_KT(const orc_mpc *mp);
+int   orc_mpc_last_successful_solve(const orc_mpc *mp);
 
 int   orc_fma_mode(void); /* the ORACLE_FMA this library was built with */
 

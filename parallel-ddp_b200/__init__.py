@@ -33,13 +33,13 @@ class Config(C.Structure):
                 ("alpha_base", C.c_float), ("total_time", C.c_float),
                 ("rho_init", C.c_float), ("rho_min", C.c_float), ("rho_max", C.c_float), ("rho_factor", C.c_float),
                 ("exp_red_min", C.c_float), ("exp_red_max", C.c_float), ("max_defect", C.c_float), ("tol_cost", C.c_float),
-                ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float)]
+                ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float), ("gravity", C.c_float)]
 
 
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -76,6 +76,8 @@ def load_library():
     L.pddp_selftest_rcp.argtypes = [C.POINTER(C.c_ulonglong)]
     L.pddp_set_warm_start.argtypes = [H, FP, FP, FP, FP]
     L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
+    L.pddp_mpc_init.argtypes = [H, FP, FP]
+    L.pddp_mpc_step.argtypes = [H, FP, FP, IP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, IP, IP, IP]
     _lib = L
     return L
 
@@ -140,6 +142,27 @@ class Solver:
             raise PddpError(f"{what} failed ({rc}): {self.L.pddp_last_error(self.h).decode()}")
 
     # ---- solver entry point -------------------------------------------------------------------------------------
+    # ---- receding horizon (runiLQR_MPC_GPU) -------------------------------------------------------------------------
+    def mpc_init(self, x_init, u_init):
+        """Start plan of the receding-horizon loop: x_init [B,N,14], u_init [B,N,7]; they also become the published plan."""
+        B, N = self.cfg.batch, self.cfg.N
+        self.mpc_x, px = _f(np.broadcast_to(x_init, (B, N, 14)).copy()); self.mpc_u, pu = _f(np.broadcast_to(u_init, (B, N, 7)).copy())
+        self.mpc_KT = np.zeros((B, N, 98), np.float32)
+        self._ck(self.L.pddp_mpc_init(self.h, px, pu), "pddp_mpc_init")
+
+    def mpc_step(self, xActual, xGoal, shiftAmount, max_iter, clear_vars=0, ignoreFirstDefectFlag=0):
+        """One runiLQR_MPC_GPU call per problem.  Returns dict(x, u, KT (the published plan, updated in place), Jout, alphaOut, iters,
+        last_successful_solve)."""
+        B = self.cfg.batch; L1 = self.cfg.max_iter + 1
+        xa, pxa = _f(np.broadcast_to(xActual, (B, 14))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        sh = np.ascontiguousarray(np.broadcast_to(shiftAmount, (B,)), dtype=np.int32)
+        Jout = np.empty((B, L1), np.float32); aOut = np.empty((B, L1), np.int32); iters = np.empty(B, np.int32); lss = np.empty(B, np.int32)
+        rc = self.L.pddp_mpc_step(self.h, pxa, pg, sh.ctypes.data_as(IP), max_iter, clear_vars, ignoreFirstDefectFlag,
+                                  self.mpc_x.ctypes.data_as(FP), self.mpc_u.ctypes.data_as(FP), self.mpc_KT.ctypes.data_as(FP),
+                                  Jout.ctypes.data_as(FP), aOut.ctypes.data_as(IP), iters.ctypes.data_as(IP), lss.ctypes.data_as(IP))
+        self._ck(rc, "pddp_mpc_step")
+        return dict(x=self.mpc_x, u=self.mpc_u, KT=self.mpc_KT, Jout=Jout, alphaOut=aOut, iters=iters, last_successful_solve=lss)
+
     def set_warm_start(self, KT0, P0, p0, d0):
         """runiLQR_GPU's KT0, P0, p0, d0: [B,N,98], [B,N,196], [B,N,14], [B,N,14] in the reference layouts."""
         B, N = self.cfg.batch, self.cfg.N

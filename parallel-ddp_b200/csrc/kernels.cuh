@@ -26,6 +26,7 @@ constexpr int AB_STRIDE = 296, H_STRIDE = 444, G_STRIDE = 24;
 struct DevState {
     // sizes
     int B, N, A, M, n, m, max_iter;
+    int iter_cap;                  // iteration limit of this solve (<= max_iter; runiLQR_MPC_GPU's max_iter argument)
     float dt, tol_cost, two_tol;
     float rho_min, rho_max, rho_factor, inv_rho_factor, exp_red_min, exp_red_max, max_defect;
     float Q1, Q2, R, QF1, QF2;
@@ -45,6 +46,7 @@ struct DevState {
     int *iter, *alphaIndex, *ignore_defect, *done, *accepted, *final_src;
     float *Jout; int *alphaOut;    // [B][max_iter+1]
     int *n_active;                 // [1]
+    float grav;                    // gravity constant of the plant (9.81; 0 in the reference's MPC_MODE)
     int rolled_out;                // this solve started with loadVarsGPU's forward rollout
     long long *dbg;                // [4096] stage clocks of CTA 0 (only written by -DPDDP_BP_TRACE builds)
 };
@@ -586,7 +588,7 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
     const bool live = a < n_cand;                              // odd count: the last half-warp replays the last candidate without storing
     if (!live){ a = n_cand - 1; }
     SimGroupSmem &s = gsm[w*GPW + grp];
-    kuka::init_ws<LANES>(s.ws, nullptr, sTb);
+    kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
     const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (w < S.M - 1) ? NBF : NBF - 1;
     const float alpha = S.alpha[a], dt = S.dt;
@@ -731,7 +733,7 @@ __global__ void select_kernel(DevState S, int mode, int b0){
         dJ = DIV(dJ, prevJ); S.prevJ[b] = sJ[alphaIndex]; alphaOut[iter] = alphaIndex; Jout[iter] = sJ[alphaIndex]; accepted = 1;
         if (dJ < S.tol_cost){ done = 1; }
     }
-    if (!done){ if (iter == S.max_iter){ done = 1; } else { iter += 1; } }
+    if (!done){ if (iter == S.iter_cap){ done = 1; } else { iter += 1; } }
     S.dJ[b] = dJ; S.rho[b] = rho; S.drho[b] = drho; S.alphaIndex[b] = alphaIndex; S.accepted[b] = accepted; S.iter[b] = iter;
     if (done){ S.done[b] = 1; S.final_src[b] = accepted ? alphaIndex : -1; atomicSub(S.n_active, 1); }
 }
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
 #endif
     if (b >= b0 + nb || S.done[b]){ return; }
     NisGroupSmem &s = gsm[w*GPW + grp];
-    kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
+    kuka::init_ws<LANES>(s.ws, &s.gs, sTb, S.grav);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
     const bool acc = (mode == 2) || ((mode == 0) && S.accepted[b]);      // mode 2: initialisation after a forward rollout
     const int a = S.alphaIndex[b];
@@ -781,7 +783,10 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         const float xold = gxp[l];
         const float xv = acc ? cx[l] : xold; s.x[l] = xv;
         gxp2[l] = (mode == 2) ? xv : xold;                         // xp2 <- xp (fpHelpers.cuh:371); initAlgGPU sets both to the start trajectory (nisInitHelpers.cuh:378-379)
-        if (acc){ gxp[l] = xv; gdp[l] = cd[l]; }
+        // defects: a candidate's array is the broadcast copy of dp (memcpyCurrAKern, nisInitHelpers.cuh:22-32) with the interval-
+        // boundary entries rewritten by the simulation, so only those change hands; the others are never read by a solve but the
+        // receding-horizon shift moves them onto boundaries later
+        if (acc){ gxp[l] = xv; if (((k+1) % (N / S.M)) == 0 && k < N-1){ gdp[l] = cd[l]; } }
     }
     if (l < m){ const float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }
     __syncwarp();
@@ -827,9 +832,105 @@ __global__ void store_kernel(DevState S, float *x_out, float *u_out, int *iters_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// receding horizon (MPCHelpers.cuh): load step of runiLQR_MPC_GPU, one CTA per problem
+// ------------------------------------------------------------------------------------------------------------------
+struct MpcState {
+    float *cx, *cu, *cd;           // [B][N][.] the current plan with its defects (h_d_x/u/d[alphaIndex] of the reference)
+    float *x_old, *u_old, *KT_old; // the shifted previous plan, restored when a solve takes no step
+    float *tmp;                    // [B][N*n*n] scratch of the out-of-place shifts
+    const float *xActual;          // [B][n]
+    const int *shift, *clear;      // [B]
+};
+// shiftAndCopy (MPCHelpers.cuh:425-453): A[k] <- A[min(shift + k, dimN-1)] for k < dimN-1 (zero past the end with `flag`), B likewise
+__device__ __forceinline__ void mpc_shift(float *A, float *tmp, int shift, int sz, int dimN, bool flag, float *B){
+    const int cnt = (dimN - 1)*sz;
+    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x){
+        const int k = idx / sz, i = idx - k*sz; int ksrc = shift + k; if (ksrc > dimN - 1){ ksrc = dimN - 1; }
+        tmp[idx] = (flag && ksrc >= dimN - 1) ? 0.f : A[(size_t)ksrc*sz + i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x){ const float v = tmp[idx]; A[idx] = v; if (B){ B[idx] = v; } }
+    __syncthreads();
+}
+__device__ __forceinline__ void mpc_zero(float *A, int cnt){ for (int i = threadIdx.x; i < cnt; i += blockDim.x){ A[i] = 0.f; } }
+__device__ __forceinline__ void mpc_copy(float *D, const float *A, int cnt){ for (int i = threadIdx.x; i < cnt; i += blockDim.x){ D[i] = A[i]; } }
+
+// loadVarsGPU_MPC (MPCHelpers.cuh:602-657) followed by the hand-over initAlgGPU does (xp, up, dp <- current plan)
+__global__ void mpc_load_kernel(DevState S, MpcState Q, int cur){
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES;
+    const int b = blockIdx.x, N = S.N, shift = Q.shift[b]; const bool clear = Q.clear[b] != 0;
+    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
+    float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
+    float *P0 = S.Pbuf[0] + (size_t)b*N*n*n, *P1 = S.Pbuf[1] + (size_t)b*N*n*n, *p0 = S.pbuf[0] + (size_t)b*N*n, *p1 = S.pbuf[1] + (size_t)b*N*n;
+    if (shift > 0){
+        mpc_shift(cx, tmp, shift, n, N, false, xp);
+        mpc_shift(cd, tmp, shift, n, N, false, nullptr);
+        if (!clear){
+            mpc_shift(cu, tmp, shift, m, N-1, true, up);
+            mpc_shift(KT, tmp, shift, n*m, N-1, true, nullptr);
+            mpc_shift(P0, tmp, shift, n*n, N, false, nullptr); mpc_shift(P1, tmp, shift, n*n, N, false, nullptr);
+            mpc_shift(p0, tmp, shift, n, N, false, nullptr); mpc_shift(p1, tmp, shift, n, N, false, nullptr);
+        }
+    }
+    if (clear){ mpc_zero(cu, N*m); mpc_zero(KT, N*n*m); mpc_zero(P0, N*n*n); mpc_zero(P1, N*n*n); mpc_zero(p0, N*n); mpc_zero(p1, N*n); }
+    mpc_zero(S.du + (size_t)b*N*m, N*m); mpc_zero(S.dT + (size_t)b*S.A, S.A);
+    __syncthreads();
+    // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon.  The plant code is
+    // group-collective over whole warps, so warp 0 runs it with all its lane groups on the same problem (only group 0 stores).
+    if (threadIdx.x < 32){
+        constexpr int GPW = 32 / LANES;
+        float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
+        SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
+        const int grp = threadIdx.x / LANES, l = threadIdx.x & (LANES-1); const bool st = (grp == 0);
+        SimGroupSmem &s = gsm[grp < GPW ? grp : 0];
+        for (int i = threadIdx.x; i < 36*kuka::NB; i += 32){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
+        __syncwarp();
+        kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
+        const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
+        if (l < n){ const float v = Q.xActual[b*n + l]; s.x[l] = v; if (st){ cx[l] = v; } }
+        for (int k = 0; k < N-1; k++){
+            if (l < m){ s.u[l] = cu[k*m + l]; }
+            __syncwarp();
+            kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
+            if (l < kuka::NB){ s.xn[l] = FMA(S.dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(S.dt, s.qdd[l], s.x[l+kuka::NB]); }
+            __syncwarp();
+            if (l < n){ const float v = s.xn[l]; s.x[l] = v; if (st){ cx[(k+1)*n + l] = v; } }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    mpc_copy(Q.x_old + (size_t)b*N*n, xp, N*n); mpc_copy(Q.u_old + (size_t)b*N*m, up, N*m); mpc_copy(Q.KT_old + (size_t)b*N*n*m, KT, N*n*m);
+    __syncthreads();
+    mpc_copy(xp, cx, N*n); mpc_copy(up, cu, N*m); mpc_copy(dp, cd, N*n);
+}
+// storeVarsGPU_MPC (:755-776) on the device side: success[b] != 0 -> the final trajectory becomes the current plan, else the
+// shifted previous plan and gains come back
+__global__ void mpc_store_kernel(DevState S, MpcState Q, const int *success, float *x_out, float *u_out, float *KT_out){
+    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m;
+    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
+    const int src = S.final_src[b];
+    const float *sx = (src >= 0) ? S.x + ((size_t)b*S.A + src)*N*n : S.xp + (size_t)b*N*n;
+    const float *su = (src >= 0) ? S.u + ((size_t)b*S.A + src)*N*m : S.up + (size_t)b*N*m;
+    // defects of the current plan: a candidate's array is the broadcast copy of dp (memcpyCurrAKern) with its interval-boundary
+    // entries rewritten by the simulation; the other entries are never read by a solve but they shift onto boundaries later
+    const float *sdc = S.d + ((size_t)b*S.A + (src >= 0 ? src : 0))*N*n, *sdp = S.dp + (size_t)b*N*n; const int NBF = N / S.M;
+    auto sd_at = [&](int i){ const int k = i / n; const bool onb = (((k+1) % NBF) == 0) && (k < N-1); return (src >= 0 && onb) ? sdc[i] : sdp[i]; };
+    if (success[b]){
+        for (int i = threadIdx.x; i < N*n; i += blockDim.x){ const float v = sx[i]; cx[i] = v; x_out[(size_t)b*N*n + i] = v; cd[i] = sd_at(i); }
+        for (int i = threadIdx.x; i < N*m; i += blockDim.x){ const float v = su[i]; cu[i] = v; u_out[(size_t)b*N*m + i] = v; }
+        for (int i = threadIdx.x; i < N*n*m; i += blockDim.x){ KT_out[(size_t)b*N*n*m + i] = KT[i]; }
+    } else {
+        for (int i = threadIdx.x; i < N*n; i += blockDim.x){ cx[i] = Q.x_old[(size_t)b*N*n + i]; cd[i] = sd_at(i); }
+        for (int i = threadIdx.x; i < N*m; i += blockDim.x){ cu[i] = Q.u_old[(size_t)b*N*m + i]; }
+        for (int i = threadIdx.x; i < N*n*m; i += blockDim.x){ KT[i] = Q.KT_old[(size_t)b*N*n*m + i]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // plug-in unit kernels (one group per sample, same group widths as the production kernels)
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void unit_dynamics_kernel(const float *I, const float *Tbody, const float *x, const float *u, int nsamp, float *qdd){
+__global__ void unit_dynamics_kernel(const float *I, const float *Tbody, float grav, const float *x, const float *u, int nsamp, float *qdd){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LANES = SIM_LANES, GPW = 32 / SIM_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
@@ -838,7 +939,7 @@ __global__ void unit_dynamics_kernel(const float *I, const float *Tbody, const f
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = I[i]; sTb[i] = Tbody[i]; }
     __syncthreads();
     SimGroupSmem &s = gsm[grp];
-    kuka::init_ws<LANES>(s.ws, nullptr, sTb);
+    kuka::init_ws<LANES>(s.ws, nullptr, sTb, grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
     for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
         const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;         // tail: replay the last sample
@@ -849,7 +950,7 @@ __global__ void unit_dynamics_kernel(const float *I, const float *Tbody, const f
         __syncwarp();
     }
 }
-__global__ void unit_gradient_kernel(const float *I, const float *Tbody, const float *x, const float *u, int nsamp, float dt, float *AB, float *qdd){
+__global__ void unit_gradient_kernel(const float *I, const float *Tbody, float grav, const float *x, const float *u, int nsamp, float dt, float *AB, float *qdd){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, nm = kuka::NX + kuka::NU, np = kuka::NB, LANES = NIS_LANES, GPW = 32 / NIS_LANES;
     float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
@@ -858,7 +959,7 @@ __global__ void unit_gradient_kernel(const float *I, const float *Tbody, const f
     for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = I[i]; sTb[i] = Tbody[i]; }
     __syncthreads();
     NisGroupSmem &s = gsm[grp];
-    kuka::init_ws<LANES>(s.ws, &s.gs, sTb);
+    kuka::init_ws<LANES>(s.ws, &s.gs, sTb, grav);
     for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
         const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;
         if (l < kuka::NX){ s.x[l] = x[k*kuka::NX + l]; } if (l < kuka::NU){ s.u[l] = u[k*kuka::NU + l]; }

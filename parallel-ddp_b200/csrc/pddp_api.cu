@@ -29,6 +29,9 @@ struct pddp_solver {
     int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
     float *w_KT = nullptr, *w_P = nullptr, *w_p = nullptr, *w_d = nullptr;     // warm-start inputs (pddp_set_warm_start)
     int next_clear = 1, next_rollout = 0;                                      // loadVarsGPU flags of the next solve
+    MpcState mpc{}; int *d_mpc_flags = nullptr; float *d_xActual = nullptr; bool mpc_ready = false;   // receding-horizon state (pddp_mpc_*)
+    std::vector<int> mpc_lss;                                                  // last_successful_solve per problem (MPCHelpers.cuh:63)
+    size_t smem_mpc = 0;
     long launches = 0;
     int n, m, num_sms = 148;
     float *d_xout = nullptr, *d_uout = nullptr; int *d_iters = nullptr;
@@ -49,6 +52,7 @@ extern "C" void pddp_default_config_kuka(pddp_config *c, int N, int batch){
     c->rho_init = (float)12.5; c->rho_min = (float)0.01; c->rho_max = (float)10000000.0; c->rho_factor = (float)1.25;
     c->exp_red_min = (float)0.05; c->exp_red_max = (float)1.25; c->max_defect = (float)1.0; c->tol_cost = 0.0f;
     c->Q1 = (float)0.1; c->Q2 = (float)0.001; c->R = (float)0.0001; c->QF1 = (float)1000.0; c->QF2 = (float)1000.0;
+    c->gravity = KUKA_GRAV;
 }
 
 extern "C" const char *pddp_last_error(pddp_handle h){ return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -89,12 +93,12 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 4; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S));
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
-    S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter;
+    S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter; S.iter_cap = cfg->max_iter;
     S.dt = (float)((double)cfg->total_time/(double)(N-1));          // (T)TIME_STEP, config.cuh:136
     S.tol_cost = cfg->tol_cost; S.two_tol = (float)(2*(double)cfg->tol_cost);
     S.rho_min = cfg->rho_min; S.rho_max = cfg->rho_max; S.rho_factor = cfg->rho_factor; S.inv_rho_factor = (float)(1.0/(double)cfg->rho_factor);
     S.exp_red_min = cfg->exp_red_min; S.exp_red_max = cfg->exp_red_max; S.max_defect = cfg->max_defect;
-    S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2;
+    S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2; S.grav = cfg->gravity;
     float *dI, *dTb, *dal;
     #define DA(ptr, count, name) do { if (dalloc(h, &(ptr), (size_t)(count), name)){ return bail(PDDP_E_CUDA); } } while (0)
     DA(dI, 252, nullptr); DA(dTb, 252, nullptr); DA(dal, PDDP_MAX_ALPHA, nullptr);
@@ -247,7 +251,7 @@ static int run_iterations(pddp_handle h, double *times_ms, int groups){
     // fork: every group stream starts after the setup on stream 0
     if (groups > 1){ CK(cudaEventRecord(h->gev[8], h->stream)); for (int g = 1; g < groups; g++){ CK(cudaStreamWaitEvent(h->gstreams[g], h->gev[8], 0)); } }
     int it_done = 0;
-    for (int it = 0; it < S.max_iter; it++){
+    for (int it = 0; it < S.iter_cap; it++){
         h->cur ^= 1;
         for (int g = 0; g < groups; g++){
             const int b0 = (int)((long)S.B*g/groups), nb = (int)((long)S.B*(g+1)/groups) - b0; cudaStream_t st = h->gstreams[g]; int rc;
@@ -351,6 +355,102 @@ __global__ void selftest_rcp_kernel(unsigned long long *bad){
     if (local){ atomicAdd(bad, local); }
 }
 }
+// ---------------------------------------------------------------------------------------------------- receding horizon
+extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_init){
+    if (!h){ return PDDP_E_INVALID; }
+    if (!x_init || !u_init){ h->err = "null input"; return PDDP_E_INVALID; }
+    DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m, A = S.A;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!h->mpc.cx){
+        auto da = [&](float **p, size_t cnt){ void *q = nullptr; if (cudaMalloc(&q, cnt*4) != cudaSuccess){ return false; } *p = (float*)q; h->allocs.push_back(q); return true; };
+        float *xa = nullptr;
+        if (!da(&h->mpc.cx, B*N*n) || !da(&h->mpc.cu, B*N*m) || !da(&h->mpc.cd, B*N*n) || !da(&h->mpc.x_old, B*N*n) || !da(&h->mpc.u_old, B*N*m) ||
+            !da(&h->mpc.KT_old, B*N*n*m) || !da(&h->mpc.tmp, B*N*n*n) || !da(&xa, B*n)){ h->err = "cudaMalloc failed (receding-horizon state)"; return PDDP_E_CUDA; }
+        h->d_xActual = xa; h->mpc.xActual = xa;
+        void *q = nullptr; CK(cudaMalloc(&q, 3*B*sizeof(int))); h->d_mpc_flags = (int*)q; h->allocs.push_back(q);
+        h->mpc.shift = h->d_mpc_flags; h->mpc.clear = h->d_mpc_flags + B;
+        h->smem_mpc = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
+        CK(cudaFuncSetAttribute(mpc_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_mpc));
+    }
+    // the state runiLQR_MPC_GPU expects to find (LCMHelpers.cuh:224-233 + the caller's set-up): the plan in the current slot and in
+    // xp/up, everything else zero
+    CK(cudaMemcpyAsync(h->mpc.cx, x_init, B*N*n*4, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(h->mpc.cu, u_init, B*N*m*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.xp, x_init, B*N*n*4, cudaMemcpyHostToDevice, h->stream)); CK(cudaMemcpyAsync(S.up, u_init, B*N*m*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->mpc.cd, 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.dp, 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.d, 0, B*A*N*n*4, h->stream));
+    CK(cudaMemsetAsync(S.xp2, 0, B*N*n*4, h->stream));
+    CK(cudaMemsetAsync(S.KT, 0, B*N*n*m*4, h->stream)); CK(cudaMemsetAsync(S.du, 0, B*N*m*4, h->stream));
+    CK(cudaMemsetAsync(S.Pbuf[0], 0, B*N*n*n*4, h->stream)); CK(cudaMemsetAsync(S.Pbuf[1], 0, B*N*n*n*4, h->stream));
+    CK(cudaMemsetAsync(S.pbuf[0], 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.pbuf[1], 0, B*N*n*4, h->stream));
+    CK(cudaMemsetAsync(h->mpc.x_old, 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(h->mpc.u_old, 0, B*N*m*4, h->stream)); CK(cudaMemsetAsync(h->mpc.KT_old, 0, B*N*n*m*4, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->mpc_lss.assign(B, 0); h->mpc_ready = true; h->cur = 0;
+    return 0;
+}
+
+extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *xGoal, const int *shiftAmount, int max_iter, int clear_vars,
+                             int ignoreFirstDefectFlag, float *x, float *u, float *KT, float *Jout, int *alphaOut, int *iters_out, int *last_successful_solve){
+    if (!h){ return PDDP_E_INVALID; }
+    if (!h->mpc_ready){ h->err = "pddp_mpc_init first"; return PDDP_E_INVALID; }
+    if (!xActual || !xGoal || !shiftAmount || !x || !u || !KT){ h->err = "null input"; return PDDP_E_INVALID; }
+    DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m, L = S.max_iter + 1; int rc;
+    if (max_iter < 1 || max_iter > S.max_iter){ h->err = "max_iter of the step must be in [1, config max_iter]"; return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    h->launches = 0;
+    std::vector<int> flags(3*(size_t)B);
+    for (int b = 0; b < B; b++){
+        if (shiftAmount[b] < 0){ h->err = "negative shiftAmount"; return PDDP_E_INVALID; }
+        flags[b] = shiftAmount[b];
+        flags[B + b] = (h->mpc_lss[b] > 10 /* SOLVES_TO_RESET, MPCHelpers.cuh:34-36 */ || clear_vars) ? 1 : 0;
+    }
+    CK(cudaMemcpyAsync(h->d_mpc_flags, flags.data(), 2*(size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_xActual, xActual, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(S.xGoal, xGoal, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
+    // loadVarsGPU_MPC + hand-over; the cost-to-go buffers keep their roles: the first backward pass must seed its blocks from the
+    // shifted Pp (the older buffer) and overwrite P (the newer one), so the flip that precedes it has to land on the newer buffer
+    mpc_load_kernel<<<B, 256, h->smem_mpc, h->stream>>>(S, h->mpc, h->cur);
+    h->launches += 1; CK(cudaGetLastError());
+    const int cur_keep = h->cur ^ 1;
+    reset_kernel<<<B, 128, 0, h->stream>>>(S, h->cfg.rho_init, ignoreFirstDefectFlag);
+    h->launches += 1; CK(cudaGetLastError());
+    h->cur = cur_keep;
+    if ((rc = launch_init(h, 0))){ return rc; }
+    S.iter_cap = max_iter;
+    rc = run_iterations(h, nullptr, 1);
+    S.iter_cap = S.max_iter;
+    if (rc){ return rc; }
+    // success bookkeeping (MPCHelpers.cuh:987-991, 757-758) needs the step-size trace on the host
+    std::vector<int> aout((size_t)B*L), its(B); std::vector<float> jout((size_t)B*L);
+    CK(cudaMemcpyAsync(aout.data(), S.alphaOut, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(jout.data(), S.Jout, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(its.data(), S.iter, (size_t)B*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; b++){
+        for (int i = 1; i <= its[b]; i++){ if (aout[(size_t)b*L + i] > 0){ h->mpc_lss[b] = 0; } }
+        h->mpc_lss[b] += 1;
+        flags[2*(size_t)B + b] = (h->mpc_lss[b] == 1) ? 1 : 0;
+    }
+    CK(cudaMemcpyAsync(h->d_mpc_flags + 2*(size_t)B, flags.data() + 2*(size_t)B, (size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // results of the successful problems land in pinned staging first, the others keep the caller's previous plan
+    float *sx = h->h_stage, *su = sx + (size_t)B*N*n;
+    float *dKT = h->mpc.tmp;     // the shift scratch doubles as the device-side staging of the published gains
+    mpc_store_kernel<<<B, 256, 0, h->stream>>>(S, h->mpc, h->d_mpc_flags + 2*(size_t)B, h->d_xout, h->d_uout, dKT);
+    h->launches += 1; CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(sx, h->d_xout, (size_t)B*N*n*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(su, h->d_uout, (size_t)B*N*m*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<float> kt((size_t)N*n*m);
+    for (int b = 0; b < B; b++){
+        if (flags[2*(size_t)B + b]){
+            std::memcpy(x + (size_t)b*N*n, sx + (size_t)b*N*n, (size_t)N*n*4); std::memcpy(u + (size_t)b*N*m, su + (size_t)b*N*m, (size_t)N*m*4);
+            CK(cudaMemcpy(KT + (size_t)b*N*n*m, dKT + (size_t)b*N*n*m, (size_t)N*n*m*4, cudaMemcpyDeviceToHost));
+        }
+        if (last_successful_solve){ last_successful_solve[b] = h->mpc_lss[b]; }
+        if (iters_out){ iters_out[b] = its[b]; }
+    }
+    if (Jout){ std::memcpy(Jout, jout.data(), (size_t)B*L*4); } if (alphaOut){ std::memcpy(alphaOut, aout.data(), (size_t)B*L*4); }
+    return 0;
+}
+
 extern "C" int pddp_set_warm_start(pddp_handle h, const float *KT0, const float *P0, const float *p0, const float *d0){
     if (!h){ return PDDP_E_INVALID; }
     if (!KT0 || !P0 || !p0 || !d0){ h->err = "null warm-start array"; return PDDP_E_INVALID; }
@@ -417,7 +517,7 @@ extern "C" int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u,
     float *dx, *du, *dq;
     CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4));
     CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
-    unit_dynamics_kernel<<<nsamp < 1184 ? nsamp : 1184, 32, h->smem_udyn, h->stream>>>(h->S.I, h->S.Tbody, dx, du, nsamp, dq);
+    unit_dynamics_kernel<<<nsamp < 1184 ? nsamp : 1184, 32, h->smem_udyn, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, dq);
     CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(du); cudaFree(dq);
@@ -429,7 +529,7 @@ extern "C" int pddp_unit_integrator_gradient(pddp_handle h, const float *x, cons
     float *dx, *du, *dq, *dab;
     CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4)); CK(cudaMalloc(&dab, (size_t)nsamp*294*4));
     CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
-    unit_gradient_kernel<<<nsamp < 888 ? nsamp : 888, 32, h->smem_ugrad, h->stream>>>(h->S.I, h->S.Tbody, dx, du, nsamp, h->S.dt, dab, dq);
+    unit_gradient_kernel<<<nsamp < 888 ? nsamp : 888, 32, h->smem_ugrad, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, h->S.dt, dab, dq);
     CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(AB, dab, (size_t)nsamp*294*4, cudaMemcpyDeviceToHost));
     if (qdd){ CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost)); }

@@ -25,7 +25,7 @@ _DROP = re.compile(r"it\d+\.(nis|init)\.[xud]([1-9]|1\d)$")
 
 
 def run(N, *args):
-    exe = os.path.join(REF, f"ref_driver_N{N}")
+    exe = os.path.join(REF, f"ref_mpc_N{N}" if args and args[0] == "mpc" else f"ref_driver_N{N}")
     print("+", exe, *args, flush=True)
     subprocess.run([exe, *[str(a) for a in args]], check=True, stdout=subprocess.DEVNULL)
 
@@ -50,7 +50,10 @@ def jobs(hw):
                 (32, ("solve", "G", 0, 16, 0.0), "solve_G_N32_s0-15_tol0"),
                 # warm starts of loadVarsGPU: cold solve (tol 1e-4), then (rollout, clear) = (1,0), (0,0), (1,1) from a perturbed start
                 (32, ("warm", "G", 1, 0.0001, 0.0), "warm_G_N32_s1"),
-                (128, ("warm", "G", 2, 0.0001, 0.0001), "warm_G_N128_s2")]
+                (128, ("warm", "G", 2, 0.0001, 0.0001), "warm_G_N128_s2"),
+                # receding horizon: runiLQR_MPC_GPU (MPC_MODE build, gravity 0): seed, steps, knots shifted per step, iteration cap
+                (32, ("mpc", 5, 8, 2, 4), "mpc_G_N32_s5"),
+                (128, ("mpc", 6, 5, 3, 6), "mpc_G_N128_s6")]
     return out
 
 

@@ -20,7 +20,7 @@ class Cfg(C.Structure):
                 ("rho_init", F), ("rho_min", F), ("rho_max", F), ("rho_factor", F),
                 ("exp_red_min", F), ("exp_red_max", F), ("max_defect", F), ("tol_cost", F),
                 ("Q1", F), ("Q2", F), ("R", F), ("QF1", F), ("QF2", F),
-                ("I", F * 252), ("Tbody", F * 252)]
+                ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float)]
 
 
 class Ws(C.Structure):
@@ -76,6 +76,12 @@ def lib(fma=False):
         getattr(L, fn).argtypes = [cp, wp]
     L.orc_accept_reject.argtypes = [cp, wp, FP, IP]; L.orc_accept_reject.restype = C.c_int
     L.orc_solve.argtypes = [cp, FP, FP, FP, FP, FP, FP, IP]; L.orc_solve.restype = C.c_int
+    L.orc_mpc_alloc.argtypes = [cp, FP, FP, FP]; L.orc_mpc_alloc.restype = C.c_void_p
+    L.orc_mpc_free.argtypes = [C.c_void_p]
+    L.orc_mpc_step.argtypes = [cp, C.c_void_p, FP, FP, C.c_int, C.c_int, C.c_int, C.c_int, FP, IP]; L.orc_mpc_step.restype = C.c_int
+    for _f in ('orc_mpc_x', 'orc_mpc_u', 'orc_mpc_KT'):
+        getattr(L, _f).argtypes = [C.c_void_p]; getattr(L, _f).restype = FP
+    L.orc_mpc_last_successful_solve.argtypes = [C.c_void_p]; L.orc_mpc_last_successful_solve.restype = C.c_int
     L.orc_solve_ex.argtypes = [cp, FP, FP, FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, IP]; L.orc_solve_ex.restype = C.c_int
     L.orc_fma_mode.restype = C.c_int
     assert L.orc_fma_mode() == (1 if fma else 0)
