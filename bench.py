@@ -36,7 +36,9 @@ METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
 CONFIG = {"workload": "configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batch=64 per GPU, TOL_COST=0 (100 iterations per problem)",
           "plant": "kuka_iiwa14", "knots": N_KNOTS, "n_alpha": N_ALPHA, "m_blocks": M_BLOCKS, "batch_per_gpu": BATCH_PER_GPU,
-          "max_iter": MAX_ITER, "l2": "a 256 MiB buffer is rewritten between timed steps (working set 69 MB < 126 MB L2)"}
+          "max_iter": MAX_ITER, "l2": "a 256 MiB buffer is rewritten between timed steps (working set 69 MB < 126 MB L2)",
+          # every iteration does the reference's full work (rejected line searches included) unless PDDP_SKIP_UNCHANGED=1 is set
+          "skip_unchanged_gradient_refresh": bool(int(os.environ.get("PDDP_SKIP_UNCHANGED", "0") or 0))}
 
 
 def peaks():

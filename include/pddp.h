@@ -142,6 +142,11 @@ int pddp_mpc_step(pddp_handle h, const float *xActual, const float *xGoal, const
                   int ignoreFirstDefectFlag, float *x, float *u, float *KT, float *Jout, int *alphaOut, int *iters_out,
                   int *last_successful_solve);
 
+/* Opt-in (default off, env PDDP_SKIP_UNCHANGED=1): skip the gradient / cost-derivative refresh of a problem whose line search was
+ * rejected -- its trajectory, hence AB, H, g, is unchanged, results are bit-identical.  The reference recomputes them
+ * (nisInitHelpers.cuh:245-279) and the default does too, so that timed work matches the reference's iteration for iteration. */
+int pddp_set_skip_unchanged(pddp_handle h, int on);
+
 /* self-test: compares the library's reciprocal (pddp_math.cuh rcp_rn) with the IEEE division 1.0f/x the reference
  * compiles to (e.g. DDPHelpers/invHelpers.cuh pivot reciprocals) on all 2^32 float bit patterns; *mismatches = count. */
 int pddp_selftest_rcp(unsigned long long *mismatches);

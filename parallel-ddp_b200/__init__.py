@@ -39,7 +39,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -77,6 +77,7 @@ def load_library():
     L.pddp_set_warm_start.argtypes = [H, FP, FP, FP, FP]
     L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
     L.pddp_mpc_init.argtypes = [H, FP, FP]
+    L.pddp_set_skip_unchanged.argtypes = [H, C.c_int]
     L.pddp_mpc_step.argtypes = [H, FP, FP, IP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, IP, IP, IP]
     _lib = L
     return L
@@ -196,6 +197,10 @@ class Solver:
         rc = self.L.pddp_solve_device(self.h, d_x0, d_u0, d_xg, ignoreFirstDefectFlag, d_x, d_u, d_J, d_a, d_it,
                                       times.ctypes.data_as(DP) if times is not None else None)
         self._ck(rc, "pddp_solve_device")
+
+    def set_skip_unchanged(self, on):
+        """Opt-in: no gradient refresh for problems whose line search was rejected (results unchanged)."""
+        self._ck(self.L.pddp_set_skip_unchanged(self.h, int(on)), "pddp_set_skip_unchanged")
 
     def set_groups(self, groups):
         """Problem groups iterated on separate streams (overlap of latency- and throughput-bound kernels); returns the value in effect."""

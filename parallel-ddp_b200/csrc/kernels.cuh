@@ -47,6 +47,7 @@ struct DevState {
     float *Jout; int *alphaOut;    // [B][max_iter+1]
     int *n_active;                 // [1]
     float grav;                    // gravity constant of the plant (9.81; 0 in the reference's MPC_MODE)
+    int skip_unchanged;            // opt-in: skip the gradient refresh of a problem whose line search was rejected
     int rolled_out;                // this solve started with loadVarsGPU's forward rollout
     long long *dbg;                // [4096] stage clocks of CTA 0 (only written by -DPDDP_BP_TRACE builds)
 };
@@ -789,6 +790,9 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         if (acc){ gxp[l] = xv; if (((k+1) % (N / S.M)) == 0 && k < N-1){ gdp[l] = cd[l]; } }
     }
     if (l < m){ const float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }
+    // opt-in (pddp_set_skip_unchanged): after a rejected line search the trajectory, hence AB, H and g, are unchanged; the
+    // reference recomputes them all the same (nisInitHelpers.cuh:245-279) and so does the default here
+    if (S.skip_unchanged && mode == 0 && !acc){ return; }
     __syncwarp();
     // cost gradient (plants/cost_arm.cuh:156-202)
     const float *xg = S.xGoal + b*n;

@@ -28,6 +28,7 @@ struct pddp_solver {
     std::string err;
     int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
     float *w_KT = nullptr, *w_P = nullptr, *w_p = nullptr, *w_d = nullptr;     // warm-start inputs (pddp_set_warm_start)
+    bool skip_env = false;
     int next_clear = 1, next_rollout = 0;                                      // loadVarsGPU flags of the next solve
     MpcState mpc{}; int *d_mpc_flags = nullptr; float *d_xActual = nullptr; bool mpc_ready = false;   // receding-horizon state (pddp_mpc_*)
     std::vector<int> mpc_lss;                                                  // last_successful_solve per problem (MPCHelpers.cuh:63)
@@ -90,8 +91,9 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     h->gstreams.push_back(h->stream);
     for (int g = 1; g < 8; g++){ cudaStream_t st; CKC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); h->gstreams.push_back(st); }
     for (int g = 0; g < 9; g++){ cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->gev.push_back(e); }
+    { const char *env = std::getenv("PDDP_SKIP_UNCHANGED"); h->skip_env = env && std::atoi(env) != 0; }
     { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 4; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
-    DevState &S = h->S; std::memset(&S, 0, sizeof(S));
+    DevState &S = h->S; std::memset(&S, 0, sizeof(S)); S.skip_unchanged = h->skip_env ? 1 : 0;
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
     S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter; S.iter_cap = cfg->max_iter;
     S.dt = (float)((double)cfg->total_time/(double)(N-1));          // (T)TIME_STEP, config.cuh:136
@@ -469,6 +471,10 @@ extern "C" int pddp_set_warm_start(pddp_handle h, const float *KT0, const float 
     CK(cudaMemcpyAsync(h->w_d, d0, B*N*n*4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+extern "C" int pddp_set_skip_unchanged(pddp_handle h, int on){
+    if (!h){ return PDDP_E_INVALID; }
+    h->S.skip_unchanged = on ? 1 : 0; return 0;
 }
 extern "C" int pddp_set_start_mode(pddp_handle h, int forwardRolloutFlag, int clearVarsFlag){
     if (!h){ return PDDP_E_INVALID; }
