@@ -239,6 +239,19 @@ def main():
                             "algorithmic_bytes_per_problem": BP_BYTES_PER_PROBLEM},
                "phases_ms_per_step_unoverlapped": {k: float(v) / args.steps for k, v in zip(("total", "sim+select", "sweep", "bp", "nis", "init+store"), phase)},
                "wall_s_device_leg": wall_s}
+        # the two kernels that take most of an iteration are FP32-issue / latency bound: algorithmic FLOP of the
+        # reference's formulation (FMA = 2) per unit, counted with an instrumented build of the oracle (every FMA/MUL/ADD/SUB of
+        # oracle/pddp_oracle.c): forward dynamics + Euler step 12 628, + control update and cost ~= 12.9 kFLOP per (candidate,
+        # knot); analytic integrator gradient 184 059 ~= 184 kFLOP per knot --
+        # against the nominal FP32 peak 148 SM x 128 FMA/clk x 2 x SM clock
+        ph = out["phases_ms_per_step_unoverlapped"]; sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        sim_flop = B * N_ALPHA * (N_KNOTS - 1) * 12.9e3 * MAX_ITER; nis_flop = B * N_KNOTS * 184e3 * MAX_ITER
+        out["other_kernels"] = [
+            {"kernel": "sim_kernel (+select)", "bound": "fp32 issue / latency", "achieved": sim_flop / (ph["sim+select"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+             "frac": sim_flop / (ph["sim+select"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"},
+            {"kernel": "nis_kernel", "bound": "fp32 issue / latency", "achieved": nis_flop / (ph["nis"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+             "frac": nis_flop / (ph["nis"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"}]
         ncu = os.path.join(ROOT, "profiles", "bp_traffic.json")
         if os.path.exists(ncu):
             out["roofline"]["traffic"] = json.load(open(ncu)).get("dram_bytes_per_launch")
