@@ -76,6 +76,9 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+_REF_FAIL = ""
+
+
 def ref_cpu_run(nseeds, mode="P", seed0=0):
     """Unmodified reference CPU path on `nseeds` benchmark problems; returns (iters_per_sec, total_iters, seconds, cores) or None."""
     exe = os.path.join(ROOT, "oracle", "_ref", f"ref_driver_N{N_KNOTS}")
@@ -84,6 +87,8 @@ def ref_cpu_run(nseeds, mode="P", seed0=0):
     r = subprocess.run([exe, "time", mode, str(seed0), str(nseeds), "0.0"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
     m = re.search(r"REFSUMMARY (\{.*\})", r.stderr)
     if not m:
+        global _REF_FAIL
+        _REF_FAIL = f"rc={r.returncode}: " + " | ".join(r.stderr.strip().splitlines()[-2:])[:200]
         return None
     s = json.loads(m.group(1))
     return s["total_iters"] / (s["sum_solve_ms"] / 1000.0), s["total_iters"], s["sum_solve_ms"] / 1000.0, s["cores"]
@@ -110,7 +115,8 @@ def cpu_baseline(nseeds=8):
         return {"value": r[0], "unit": UNIT, "cores": r[3], "kind": "reference",
                 "sample": f"{nseeds} of the 64 benchmark problems (seeds 0..{nseeds-1}) x 100 iterations, reference runiLQR_CPU2 (std::thread parallel line search), {r[2]:.1f} s"}
     r = oracle_port_run(2)
-    return {"value": r[0], "unit": UNIT, "cores": 1, "kind": "port", "sample": f"2 benchmark problems x 100 iterations, single-threaded oracle port, {r[2]:.1f} s"}
+    return {"value": r[0], "unit": UNIT, "cores": 1, "kind": "port", "sample": f"2 benchmark problems x 100 iterations, single-threaded oracle port, {r[2]:.1f} s"
+            + (f" (the reference binary did not run on this host: {_REF_FAIL})" if _REF_FAIL else "")}
 
 
 def run_reference(args, rank):
