@@ -862,7 +862,7 @@ __device__ __forceinline__ void mpc_copy(float *D, const float *A, int cnt){ for
 // loadVarsGPU_MPC (MPCHelpers.cuh:602-657) followed by the hand-over initAlgGPU does (xp, up, dp <- current plan)
 __global__ void mpc_load_kernel(DevState S, MpcState Q, int cur){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES;
+    constexpr int n = kuka::NX, m = kuka::NU, LANES = 32;          // the rollout is one trajectory: the whole warp works on it
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b]; const bool clear = Q.clear[b] != 0;
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
     float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
@@ -880,26 +880,23 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q, int cur){
     if (clear){ mpc_zero(cu, N*m); mpc_zero(KT, N*n*m); mpc_zero(P0, N*n*n); mpc_zero(P1, N*n*n); mpc_zero(p0, N*n); mpc_zero(p1, N*n); }
     mpc_zero(S.du + (size_t)b*N*m, N*m); mpc_zero(S.dT + (size_t)b*S.A, S.A);
     __syncthreads();
-    // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon.  The plant code is
-    // group-collective over whole warps, so warp 0 runs it with all its lane groups on the same problem (only group 0 stores).
+    // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon, by warp 0
     if (threadIdx.x < 32){
-        constexpr int GPW = 32 / LANES;
         float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-        SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
-        const int grp = threadIdx.x / LANES, l = threadIdx.x & (LANES-1); const bool st = (grp == 0);
-        SimGroupSmem &s = gsm[grp < GPW ? grp : 0];
-        for (int i = threadIdx.x; i < 36*kuka::NB; i += 32){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
+        SimGroupSmem &s = *reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
+        const int l = threadIdx.x;
+        for (int i = l; i < 36*kuka::NB; i += 32){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
         __syncwarp();
         kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
         const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
-        if (l < n){ const float v = Q.xActual[b*n + l]; s.x[l] = v; if (st){ cx[l] = v; } }
+        if (l < n){ const float v = Q.xActual[b*n + l]; s.x[l] = v; cx[l] = v; }
         for (int k = 0; k < N-1; k++){
             if (l < m){ s.u[l] = cu[k*m + l]; }
             __syncwarp();
             kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
             if (l < kuka::NB){ s.xn[l] = FMA(S.dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(S.dt, s.qdd[l], s.x[l+kuka::NB]); }
             __syncwarp();
-            if (l < n){ const float v = s.xn[l]; s.x[l] = v; if (st){ cx[(k+1)*n + l] = v; } }
+            if (l < n){ const float v = s.xn[l]; s.x[l] = v; cx[(k+1)*n + l] = v; }
             __syncwarp();
         }
     }

@@ -371,7 +371,7 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
         h->d_xActual = xa; h->mpc.xActual = xa;
         void *q = nullptr; CK(cudaMalloc(&q, 3*B*sizeof(int))); h->d_mpc_flags = (int*)q; h->allocs.push_back(q);
         h->mpc.shift = h->d_mpc_flags; h->mpc.clear = h->d_mpc_flags + B;
-        h->smem_mpc = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
+        h->smem_mpc = 2*36*kuka::NB*sizeof(float) + sizeof(SimGroupSmem);
         CK(cudaFuncSetAttribute(mpc_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_mpc));
     }
     // the state runiLQR_MPC_GPU expects to find (LCMHelpers.cuh:224-233 + the caller's set-up): the plan in the current slot and in
