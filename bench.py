@@ -30,13 +30,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_KNOTS, N_ALPHA, M_BLOCKS, BATCH_PER_GPU, MAX_ITER = 128, 16, 4, 64, 100
+N_KNOTS, N_ALPHA, M_BLOCKS, BATCH_PER_GPU, MAX_ITER = 128, 16, 4, int(os.environ.get("PDDP_BENCH_BATCH", "64")), 100   # 64 = the headline; the env is for the strong-scaling data point (512 on one GPU)
 BP_BYTES_PER_PROBLEM = 4 * ((N_KNOTS - 1) * 1281 + 4 * 238 + 3 * 14 + 2 * 210 + 3 * 4)   # = 656452
 METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
-CONFIG = {"workload": "configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batch=64 per GPU, TOL_COST=0 (100 iterations per problem)",
+CONFIG = {"workload": f"configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batch={BATCH_PER_GPU} per GPU, TOL_COST=0 (100 iterations per problem)",
           "plant": "kuka_iiwa14", "knots": N_KNOTS, "n_alpha": N_ALPHA, "m_blocks": M_BLOCKS, "batch_per_gpu": BATCH_PER_GPU,
-          "max_iter": MAX_ITER, "l2": "a 256 MiB buffer is rewritten between timed steps (working set 69 MB < 126 MB L2)",
+          "max_iter": MAX_ITER, "l2": f"a 256 MiB buffer is rewritten between timed steps (working set {1.08*BATCH_PER_GPU:.0f} MB)",
           # every iteration does the reference's full work (rejected line searches included) unless PDDP_SKIP_UNCHANGED=1 is set
           "skip_unchanged_gradient_refresh": bool(int(os.environ.get("PDDP_SKIP_UNCHANGED", "0") or 0))}
 
