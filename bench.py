@@ -158,6 +158,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout carries exactly one JSON line here
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PDDP_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pddp = importlib.import_module("parallel-ddp_b200")
     B, N, L1 = BATCH_PER_GPU, N_KNOTS, MAX_ITER + 1
