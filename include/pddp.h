@@ -142,6 +142,21 @@ int pddp_mpc_step(pddp_handle h, const float *xActual, const float *xGoal, const
                   int ignoreFirstDefectFlag, float *x, float *u, float *KT, float *Jout, int *alphaOut, int *iters_out,
                   int *last_successful_solve);
 
+/* ---- trajectory hand-off format: the LCM message drake::lcmt_trajectory_f (lcmtypes/drake/lcmt_trajectory_f.hpp) the reference's
+ * MPC loop publishes to its trajectory runner (LCMHelpers.cuh:245-256).  Wire format: 8-byte fingerprint, utime (int64), x_size,
+ * u_size, KT_size (int32), then x[x_size], u[u_size], KT[KT_size] floats, everything in network byte order.  Host-only helpers;
+ * they return the number of bytes written / read or a negative PDDP_E_* code. */
+long pddp_traj_f_encoded_size(int x_size, int u_size, int KT_size);
+long pddp_traj_f_encode(long long utime, const float *x, int x_size, const float *u, int u_size, const float *KT, int KT_size,
+                        void *buf, long capacity);
+long pddp_traj_f_decode(const void *buf, long nbytes, long long *utime, int *x_size, int *u_size, int *KT_size,
+                        float *x, float *u, float *KT, long cap_x, long cap_u, long cap_KT);
+/* Exactly what LCMHelpers.cuh:245-252 builds from trajVars for `steps` = TRAJ_RUNNER_TIME_STEPS knots: the size fields are BYTE
+ * counts and the arrays are that long, data in the first quarter, zeros behind (with_feedback = USE_FEEDBACK_IN_TRAJ_RUNNER).
+ * buf == NULL returns the size needed. */
+long pddp_traj_f_pack_reference(long long utime, const float *x, const float *u, const float *KT, int steps, int with_feedback,
+                                void *buf, long capacity);
+
 /* Opt-in (default off, env PDDP_SKIP_UNCHANGED=1): skip the gradient / cost-derivative refresh of a problem whose line search was
  * rejected -- its trajectory, hence AB, H, g, is unchanged, results are bit-identical.  The reference recomputes them
  * (nisInitHelpers.cuh:245-279) and the default does too, so that timed work matches the reference's iteration for iteration. */

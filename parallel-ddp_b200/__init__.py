@@ -39,7 +39,8 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged"]
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged",
+           "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -78,6 +79,10 @@ def load_library():
     L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
     L.pddp_mpc_init.argtypes = [H, FP, FP]
     L.pddp_set_skip_unchanged.argtypes = [H, C.c_int]
+    L.pddp_traj_f_encoded_size.argtypes = [C.c_int, C.c_int, C.c_int]; L.pddp_traj_f_encoded_size.restype = C.c_long
+    L.pddp_traj_f_encode.argtypes = [C.c_longlong, FP, C.c_int, FP, C.c_int, FP, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_encode.restype = C.c_long
+    L.pddp_traj_f_decode.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_longlong), IP, IP, IP, FP, FP, FP, C.c_long, C.c_long, C.c_long]; L.pddp_traj_f_decode.restype = C.c_long
+    L.pddp_traj_f_pack_reference.argtypes = [C.c_longlong, FP, FP, FP, C.c_int, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_pack_reference.restype = C.c_long
     L.pddp_mpc_step.argtypes = [H, FP, FP, IP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, IP, IP, IP]
     _lib = L
     return L
@@ -103,6 +108,29 @@ def make_inputs_kuka(N, batch, seed0=0):
     x0 = np.zeros((batch, N, 14), np.float32); u0 = np.zeros((batch, N, 7), np.float32); xg = np.zeros((batch, 14), np.float32)
     L.pddp_make_inputs_kuka(N, batch, seed0, x0.ctypes.data_as(FP), u0.ctypes.data_as(FP), xg.ctypes.data_as(FP))
     return x0, u0, xg
+
+
+def traj_f_pack_reference(utime, x, u, KT, steps, with_feedback=True):
+    """Bytes of the lcmt_trajectory_f message the reference's MPC loop publishes for one arm (LCMHelpers.cuh:245-252)."""
+    L = load_library()
+    x, px = _f(x); u, pu = _f(u); KT, pk = _f(KT)
+    need = L.pddp_traj_f_pack_reference(utime, px, pu, pk, steps, int(with_feedback), None, 0)
+    if need < 0:
+        raise PddpError("pddp_traj_f_pack_reference: bad arguments")
+    buf = (C.c_ubyte * need)()
+    L.pddp_traj_f_pack_reference(utime, px, pu, pk, steps, int(with_feedback), buf, need)
+    return bytes(buf)
+
+
+def traj_f_decode(data):
+    """(utime, x, u, KT) of an encoded lcmt_trajectory_f message."""
+    L = load_library(); n = len(data); raw = (C.c_ubyte * n).from_buffer_copy(data)
+    t = C.c_longlong(0); xs = C.c_int(0); us = C.c_int(0); ks = C.c_int(0)
+    if L.pddp_traj_f_decode(raw, n, C.byref(t), C.byref(xs), C.byref(us), C.byref(ks), None, None, None, 0, 0, 0) < 0:
+        raise PddpError("not an lcmt_trajectory_f message")
+    x = np.zeros(xs.value, np.float32); u = np.zeros(us.value, np.float32); KT = np.zeros(ks.value, np.float32)
+    L.pddp_traj_f_decode(raw, n, None, None, None, None, x.ctypes.data_as(FP), u.ctypes.data_as(FP), KT.ctypes.data_as(FP), x.size, u.size, KT.size)
+    return int(t.value), x, u, KT
 
 
 def selftest_rcp():

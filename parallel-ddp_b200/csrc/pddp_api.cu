@@ -453,6 +453,61 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- trajectory hand-off
+// lcmt_trajectory_f (lcmtypes/drake/lcmt_trajectory_f.hpp): LCM wire format = 8-byte fingerprint, then the fields in declaration
+// order, every scalar in network byte order.  Host-only code.
+namespace {
+const unsigned long long TRAJ_F_FINGERPRINT = ((0x8fb839bd5c6031eeULL << 1) + ((0x8fb839bd5c6031eeULL >> 63) & 1));   // :256-260
+inline void put_be(unsigned char *&p, unsigned long long v, int nbytes){ for (int b = nbytes - 1; b >= 0; b--){ *p++ = (unsigned char)(v >> (8*b)); } }
+inline unsigned long long get_be(const unsigned char *&p, int nbytes){ unsigned long long v = 0; for (int b = 0; b < nbytes; b++){ v = (v << 8) | *p++; } return v; }
+inline void put_floats(unsigned char *&p, const float *src, long n_data, long n_total){
+    for (long i = 0; i < n_total; i++){ unsigned int bits = 0; if (i < n_data){ std::memcpy(&bits, &src[i], 4); } put_be(p, bits, 4); }
+}
+}
+extern "C" long pddp_traj_f_encoded_size(int x_size, int u_size, int KT_size){
+    if (x_size < 0 || u_size < 0 || KT_size < 0){ return PDDP_E_INVALID; }
+    return 8 + 8 + 3*4 + 4L*((long)x_size + u_size + KT_size);
+}
+extern "C" long pddp_traj_f_encode(long long utime, const float *x, int x_size, const float *u, int u_size, const float *KT, int KT_size,
+                                   void *buf, long capacity){
+    const long need = pddp_traj_f_encoded_size(x_size, u_size, KT_size);
+    if (need < 0 || !buf || capacity < need || (x_size && !x) || (u_size && !u) || (KT_size && !KT)){ return PDDP_E_INVALID; }
+    unsigned char *p = static_cast<unsigned char*>(buf);
+    put_be(p, TRAJ_F_FINGERPRINT, 8); put_be(p, (unsigned long long)utime, 8);
+    put_be(p, (unsigned int)x_size, 4); put_be(p, (unsigned int)u_size, 4); put_be(p, (unsigned int)KT_size, 4);
+    put_floats(p, x, x_size, x_size); put_floats(p, u, u_size, u_size); put_floats(p, KT, KT_size, KT_size);
+    return need;
+}
+extern "C" long pddp_traj_f_decode(const void *buf, long nbytes, long long *utime, int *x_size, int *u_size, int *KT_size,
+                                   float *x, float *u, float *KT, long cap_x, long cap_u, long cap_KT){
+    if (!buf || nbytes < 28){ return PDDP_E_INVALID; }
+    const unsigned char *p = static_cast<const unsigned char*>(buf);
+    if (get_be(p, 8) != TRAJ_F_FINGERPRINT){ return PDDP_E_INVALID; }
+    const long long t = (long long)get_be(p, 8); const int xs = (int)get_be(p, 4), us = (int)get_be(p, 4), ks = (int)get_be(p, 4);
+    if (xs < 0 || us < 0 || ks < 0 || nbytes < 28 + 4L*((long)xs + us + ks)){ return PDDP_E_INVALID; }
+    if (utime){ *utime = t; } if (x_size){ *x_size = xs; } if (u_size){ *u_size = us; } if (KT_size){ *KT_size = ks; }
+    auto take = [&](float *dst, long cap, int n){ for (int i = 0; i < n; i++){ unsigned int bits = (unsigned int)get_be(p, 4); if (dst && i < cap){ std::memcpy(&dst[i], &bits, 4); } } };
+    take(x, cap_x, xs); take(u, cap_u, us); take(KT, cap_KT, ks);
+    return 28 + 4L*((long)xs + us + ks);
+}
+// the message the reference's MPC loop publishes (LCMHelpers.cuh:245-252): the *_size fields carry BYTE counts
+// (ld * TRAJ_RUNNER_TIME_STEPS * sizeof(float)), the arrays have that many floats with the data in their first quarter and zeros
+// behind; without feedback (USE_FEEDBACK_IN_TRAJ_RUNNER 0) x and KT are empty.  buf == NULL returns the size needed.
+extern "C" long pddp_traj_f_pack_reference(long long utime, const float *x, const float *u, const float *KT, int steps, int with_feedback,
+                                           void *buf, long capacity){
+    if (steps < 1 || !u || (with_feedback && (!x || !KT))){ return PDDP_E_INVALID; }
+    const int n = kuka::NX, m = kuka::NU;
+    const int u_size = m*steps*4, x_size = with_feedback ? n*steps*4 : 0, KT_size = with_feedback ? n*m*steps*4 : 0;
+    const long need = pddp_traj_f_encoded_size(x_size, u_size, KT_size);
+    if (!buf){ return need; }
+    if (capacity < need){ return PDDP_E_INVALID; }
+    unsigned char *p = static_cast<unsigned char*>(buf);
+    put_be(p, TRAJ_F_FINGERPRINT, 8); put_be(p, (unsigned long long)utime, 8);
+    put_be(p, (unsigned int)x_size, 4); put_be(p, (unsigned int)u_size, 4); put_be(p, (unsigned int)KT_size, 4);
+    put_floats(p, x, with_feedback ? n*steps : 0, x_size); put_floats(p, u, m*steps, u_size); put_floats(p, KT, with_feedback ? n*m*steps : 0, KT_size);
+    return need;
+}
+
 extern "C" int pddp_set_warm_start(pddp_handle h, const float *KT0, const float *P0, const float *p0, const float *d0){
     if (!h){ return PDDP_E_INVALID; }
     if (!KT0 || !P0 || !p0 || !d0){ h->err = "null warm-start array"; return PDDP_E_INVALID; }

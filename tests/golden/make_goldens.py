@@ -65,6 +65,10 @@ def main():
             b = os.path.join(tmp, name + ".bin")
             run(N, *args, b)
             to_npz(b, os.path.join(HERE, name + ".npz"))
+        # trajectory hand-off message (lcmt_trajectory_f) built and encoded by the reference's generated type
+        for fb in (1, 0):
+            out = os.path.join(HERE, f"lcm_traj_f_N8_{'fb' if fb else 'nofb'}.bin")
+            subprocess.run([os.path.join(REF, "ref_lcm_traj"), "8", str(fb), out], check=True, stdout=subprocess.DEVNULL)
         d = refdump.load(os.path.join(tmp, "unit_H.bin"))
         np.savez(os.path.join(HERE, "kuka_model.npz"), I=d["I"], Tbody=d["Tbody"])
     elif mode == "gpu":

@@ -1,0 +1,64 @@
+"""Trajectory hand-off format: drake::lcmt_trajectory_f as the reference's MPC loop publishes it
+(LCMHelpers.cuh:245-256).  The golden bytes were produced by the reference's own generated type
+(lcmtypes/drake/lcmt_trajectory_f.hpp) in oracle/ref_harness/ref_lcm_traj.cpp; the LCM core primitives under it are a
+stand-in (third-party lcm_coretypes.h is absent: that part of the parity is unpinned, see oracle/ref_harness/lcm_stub)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pddp = importlib.import_module("parallel-ddp_b200")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _inputs(N):
+    x = (0.001 * np.arange(14 * N, dtype=np.float32) - 0.5).astype(np.float32)
+    u = (0.25 * (np.arange(7 * N) % 17) - 1).astype(np.float32)
+    KT = (1.0 / (np.arange(98 * N, dtype=np.float32) + 3)).astype(np.float32)
+    return x, u, KT
+
+
+@pytest.mark.parametrize("fb", [1, 0])
+def test_pack_matches_reference_bytes(fb):
+    N = 8
+    x, u, KT = _inputs(N)
+    ref = open(os.path.join(GOLD, f"lcm_traj_f_N8_{'fb' if fb else 'nofb'}.bin"), "rb").read()
+    mine = pddp.traj_f_pack_reference(1234567890123, x, u, KT, N, fb)
+    assert mine == ref
+    # fingerprint = the constant of lcmt_trajectory_f.hpp:258 rotated left by one, big endian
+    h = 0x8fb839bd5c6031ee; fp = ((h << 1) & 0xFFFFFFFFFFFFFFFF) + (h >> 63)
+    assert mine[:8] == fp.to_bytes(8, "big")
+    t, dx, du, dk = pddp.traj_f_decode(ref)
+    assert t == 1234567890123
+    # the reference writes BYTE counts into the size fields: arrays are 4x too long, data in the first quarter, zeros behind
+    assert du.size == 7 * N * 4 and np.array_equal(du[:7 * N], u) and not du[7 * N:].any()
+    if fb:
+        assert dx.size == 14 * N * 4 and np.array_equal(dx[:14 * N], x) and dk.size == 98 * N * 4 and np.array_equal(dk[:98 * N], KT)
+    else:
+        assert dx.size == 0 and dk.size == 0
+
+
+def test_encode_decode_round_trip_and_errors():
+    import ctypes as C
+    L = pddp.load_library()
+    rng = np.random.default_rng(0)
+    for nx, nu, nk in ((0, 0, 0), (3, 0, 5), (14 * 128, 7 * 128, 98 * 128)):
+        x = rng.standard_normal(nx).astype(np.float32); u = rng.standard_normal(nu).astype(np.float32); k = rng.standard_normal(nk).astype(np.float32)
+        need = L.pddp_traj_f_encoded_size(nx, nu, nk)
+        assert need == 28 + 4 * (nx + nu + nk)
+        buf = (C.c_ubyte * need)()
+        fp = lambda a: a.ctypes.data_as(pddp.FP) if a.size else None
+        assert L.pddp_traj_f_encode(-5, fp(x), nx, fp(u), nu, fp(k), nk, buf, need) == need
+        assert L.pddp_traj_f_encode(-5, fp(x), nx, fp(u), nu, fp(k), nk, buf, need - 1) < 0          # short buffer
+        t, dx, du, dk = pddp.traj_f_decode(bytes(buf))
+        assert t == -5 and np.array_equal(dx, x) and np.array_equal(du, u) and np.array_equal(dk, k)
+        bad = bytearray(bytes(buf)); bad[0] ^= 0xFF
+        with pytest.raises(pddp.PddpError):
+            pddp.traj_f_decode(bytes(bad))                                                            # wrong fingerprint
+        if need > 28:
+            with pytest.raises(pddp.PddpError):
+                pddp.traj_f_decode(bytes(buf)[:-1])                                                   # truncated
