@@ -47,6 +47,12 @@ typedef struct pddp_config {
     float tol_cost;                                    /* TOL_COST (config.cuh:85-87) */
     float Q1, Q2, R, QF1, QF2;                         /* plants/cost_arm.cuh:96-103 */
     float gravity;                                     /* GRAVITY (dynamics_arm.cuh:42-46): 9.81, or 0 for the reference's MPC_MODE builds */
+    int   ee_cost;                                     /* EE_COST (config.cuh:165-167): 1 = end-effector pose cost -- xGoal[b][0..5] is the goal
+                                                          pose [x y z roll pitch yaw] (the other n-6 floats of a problem's slot are ignored) and
+                                                          the weights below replace Q1..QF2; 0 = joint-space cost */
+    float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE;          /* plants/cost_arm.cuh:106-111: running / final weights of the position (1) and
+                                                          orientation (2) errors, control weight */
+    float Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;              /* cost_arm.cuh:112-115: running / final weights on joint velocities (xd) and angles (x) */
 } pddp_config;
 
 typedef struct pddp_solver *pddp_handle;

@@ -13,7 +13,8 @@
 //
 // Compile-time macros of config.cuh are honoured as the front-end of the run-time pddp_config:
 //   NUM_TIME_STEPS, NUM_ALPHA, ALPHA_BASE, M_BLOCKS, MAX_ITER, TOL_COST, TOTAL_TIME, RHO_INIT, RHO_MIN, RHO_MAX,
-//   RHO_FACTOR, EXP_RED_MIN, EXP_RED_MAX, MAX_DEFECT_SIZE, _Q1, _Q2, _R, _QF1, _QF2   (PLANT must be 4, EE_COST 0).
+//   RHO_FACTOR, EXP_RED_MIN, EXP_RED_MAX, MAX_DEFECT_SIZE, _Q1, _Q2, _R, _QF1, _QF2, EE_COST with _Q_EE1 ... _QF_xEE   (PLANT must be 4;
+//   with EE_COST 1 the caller's 6-float goal pose is what xGoal holds, as in the reference).
 #pragma once
 #include "pddp.h"
 #include <cuda_runtime.h>
@@ -31,8 +32,16 @@
 #ifndef EE_COST
 #define EE_COST 0
 #endif
-#if EE_COST
-#error "pddp_shim.cuh: the end-effector cost path is not built (SURVEY 8f-3)"
+#ifndef _Q_EE1                 // plants/cost_arm.cuh:106-117
+#define _Q_EE1 0.1
+#define _Q_EE2 0
+#define _R_EE 0.0001
+#define _QF_EE1 1000.0
+#define _QF_EE2 0
+#define _Q_xdEE 0.1
+#define _QF_xdEE 1000.0
+#define _Q_xEE 0.0
+#define _QF_xEE 0.0
 #endif
 typedef float algType;
 #define NUM_POS 7
@@ -112,11 +121,13 @@ void allocateMemory_GPU(T ***d_x, T ***h_d_x, T **d_xp, T **d_xp2, T ***d_u, T *
     cfg.total_time = (float)TOTAL_TIME; cfg.rho_init = (float)RHO_INIT; cfg.rho_min = (float)RHO_MIN; cfg.rho_max = (float)RHO_MAX; cfg.rho_factor = (float)RHO_FACTOR;
     cfg.exp_red_min = (float)EXP_RED_MIN; cfg.exp_red_max = (float)EXP_RED_MAX; cfg.max_defect = (float)MAX_DEFECT_SIZE;
     cfg.Q1 = (float)_Q1; cfg.Q2 = (float)_Q2; cfg.R = (float)_R; cfg.QF1 = (float)_QF1; cfg.QF2 = (float)_QF2;
+    cfg.ee_cost = EE_COST; cfg.Q_EE1 = (float)_Q_EE1; cfg.Q_EE2 = (float)_Q_EE2; cfg.QF_EE1 = (float)_QF_EE1; cfg.QF_EE2 = (float)_QF_EE2; cfg.R_EE = (float)_R_EE;
+    cfg.Q_xdEE = (float)_Q_xdEE; cfg.QF_xdEE = (float)_QF_xdEE; cfg.Q_xEE = (float)_Q_xEE; cfg.QF_xEE = (float)_QF_xEE;
     pddp_handle h = nullptr;
     if (pddp_create(&cfg, &h) != 0){ pddp_shim_die(nullptr, "pddp_create"); }
     *d_x = reinterpret_cast<T**>(h);                                   // the handle travels in the d_x slot
     *h_d_x = nullptr; *d_xp = nullptr; *d_xp2 = nullptr; *d_u = nullptr; *h_d_u = nullptr; *d_up = nullptr; *d_xGoal = nullptr;
-    *xGoal = (T*)std::malloc(STATE_SIZE*sizeof(T));
+    *xGoal = (T*)std::calloc(STATE_SIZE, sizeof(T));                   // EE_COST: the first six floats are the goal pose
     *d_P = *d_Pp = *d_p = *d_pp = *d_AB = *d_H = *d_g = *d_KT = *d_du = nullptr; *d_d = nullptr; *h_d_d = nullptr;
     *d_dp = *d_dT = *d_dM = nullptr; *d = (T*)std::calloc(NUM_ALPHA, sizeof(T)); *d_ApBK = *d_Bdu = *d_JT = nullptr;
     *J = (T*)std::calloc(NUM_ALPHA, sizeof(T)); *d_dJexp = nullptr; *dJexp = (T*)std::calloc(2*M_BLOCKS, sizeof(T));

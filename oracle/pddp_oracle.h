@@ -45,6 +45,8 @@ typedef struct {
     float Q1, Q2, R, QF1, QF2;   /* cost_arm.cuh:96-103 weights (other plants map theirs here) */
     float I[252], Tbody[252];    /* Kuka spatial inertias / fixed joint transforms (dynamics_arm.cuh:71-427) */
     float gravity;               /* GRAVITY dynamics_arm.cuh:42-46 (9.81; 0 under MPC_MODE) */
+    int   ee_cost;               /* EE_COST config.cuh:165-167: 1 = end-effector pose cost (goal = 6 floats), 0 = joint-space cost */
+    float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;   /* cost_arm.cuh:106-117 */
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */
@@ -61,6 +63,7 @@ typedef struct {
     /* solver scalars */
     float prevJ, dJ, z, rho, drho;
     int   iter, alphaIndex, ignore_defect;
+    float JTp[ORC_MAX_ALPHA*16];   /* EE_COST: per (alpha, shooting interval) cost partials d_JT[b + alpha*M] (fpHelpers.cuh:299) */
 } orc_ws;
 
 void  orc_default_cfg_kuka(orc_cfg *c, int N);                 /* headline constants, SURVEY A.1 (I/Tbody must be filled by caller) */
@@ -77,6 +80,12 @@ void  orc_integrator(const orc_cfg *c, const float *x, const float *u, float *xn
 void  orc_integrator_gradient(const orc_cfg *c, const float *x, const float *u, float *AB, float *qdd_out);
 float orc_cost(const orc_cfg *c, const float *x, const float *u, const float *xg, int k);               /* cost_*.cuh costFunc */
 void  orc_cost_grad(const orc_cfg *c, float *H, float *g, const float *x, const float *u, const float *xg, int k);
+
+/* end-effector cost plug-ins (EE_COST 1) */
+void  orc_ee_pos(const orc_cfg *c, const float *x, float *ee /*[6]*/, float *dee /*[7][6] or NULL*/);           /* compute_eePos dynamics_arm.cuh:1877-1923 */
+float orc_ee_cost(const orc_cfg *c, const float *ee, const float *goal, const float *x, const float *u, int k);  /* costFunc cost_arm.cuh:306-325 */
+void  orc_ee_cost_grad(const orc_cfg *c, float *H, float *g, const float *ee, const float *dee, const float *goal,
+                       const float *x, const float *u, int k);                                                 /* costGrad cost_arm.cuh:328-388 */
 
 /* phases, operating on a workspace */
 void  orc_load(const orc_cfg *c, orc_ws *w, const float *x0, const float *u0, const float *xg);        /* loadVarsGPU, clear=1, rollout=0 */

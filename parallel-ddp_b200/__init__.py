@@ -26,6 +26,10 @@ class PddpError(RuntimeError):
     pass
 
 
+# the nine weights of the end-effector cost, in the order of pddp_config (plants/cost_arm.cuh:106-115)
+EE_WEIGHT_NAMES = ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")
+
+
 class Config(C.Structure):
     """pddp_config (include/pddp.h): run-time form of config.cuh."""
     _fields_ = [("plant", C.c_int), ("N", C.c_int), ("n_alpha", C.c_int), ("M", C.c_int), ("max_iter", C.c_int),
@@ -33,7 +37,8 @@ class Config(C.Structure):
                 ("alpha_base", C.c_float), ("total_time", C.c_float),
                 ("rho_init", C.c_float), ("rho_min", C.c_float), ("rho_max", C.c_float), ("rho_factor", C.c_float),
                 ("exp_red_min", C.c_float), ("exp_red_max", C.c_float), ("max_defect", C.c_float), ("tol_cost", C.c_float),
-                ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float), ("gravity", C.c_float)]
+                ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float), ("gravity", C.c_float),
+                ("ee_cost", C.c_int)] + [(k, C.c_float) for k in EE_WEIGHT_NAMES]
 
 
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",

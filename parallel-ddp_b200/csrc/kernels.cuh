@@ -50,6 +50,10 @@ struct DevState {
     int skip_unchanged;            // opt-in: skip the gradient refresh of a problem whose line search was rejected
     int rolled_out;                // this solve started with loadVarsGPU's forward rollout
     long long *dbg;                // [4096] stage clocks of CTA 0 (only written by -DPDDP_BP_TRACE builds)
+    // end-effector cost (EE_COST 1, plants/cost_arm.cuh:204-389): xGoal[b][0..5] is the goal pose, costk[b][a][0..M-1] the
+    // simulation's per-interval cost partials (fpHelpers.cuh:299)
+    int ee;
+    float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -551,6 +555,7 @@ constexpr int SIM_LANES = 16;
 struct SimGroupData {
     kuka::FwdWsT<false> ws;
     float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
+    float ee[8];               // tool pose of the current knot (EE_COST)
 };
 // The two groups of a warp run the same instruction on their own workspaces: the workspaces are padded to an odd multiple
 // of 16 banks so that a 16-lane unit-stride access of one group never meets the other group's banks.
@@ -570,6 +575,32 @@ __device__ __forceinline__ float cost_knot(const float *x, const float *u, const
     return MUL(0.5f, cost);
 }
 
+// end-effector cost terms (plants/cost_arm.cuh; USE_EE_VEL_COST, USE_LIMITS_FLAG, USE_SMOOTH_ABS 0, no xTarget, timeShift 0)
+// eeCost :207-223
+__device__ __forceinline__ float ee_pose_cost(const float *ee, const float *goal, bool fin, const DevState &S){
+    float cost = 0.f;
+    #pragma unroll
+    for (int i = 0; i < 6; i++){
+        const float dl = SUB(ee[i], goal[i]), Q = fin ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
+        cost = FMA(MUL(MUL(0.5f, Q), dl), dl, cost);
+    }
+    return cost;
+}
+// `cost += nominalStateCost(...)` :263-270
+__device__ __forceinline__ float ee_add_nominal(const float *x, int ind, bool fin, float cost, const DevState &S){
+    const float Qq = fin ? S.QF_xEE : S.Q_xEE, Qqd = fin ? S.QF_xdEE : S.Q_xdEE, dq = x[ind], dqd = x[ind + kuka::NB];
+    return FMA(0.5f, FMA(MUL(Qq, dq), dq, MUL(MUL(Qqd, dqd), dqd)), cost);
+}
+// joint `ind`'s share of one knot (split costFunc :283-303)
+__device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *u, bool fin, const DevState &S){
+    float cost = 0.f;
+    if (ind == 0){ cost = ADD(cost, ee_pose_cost(ee, goal, fin, S)); }
+    const float Rk = fin ? 0.f : S.R_EE;
+    cost = FMA(MUL(MUL(0.5f, Rk), u[ind]), u[ind], cost);
+    return ee_add_nominal(x, ind, fin, cost, S);
+}
+
+template <bool EE>
 __global__ void sim_kernel(DevState S, int b0, int n_cand){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES, GPW = 32 / SIM_LANES;
@@ -591,7 +622,9 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
     SimGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
-    const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (w < S.M - 1) ? NBF : NBF - 1;
+    // EE: every interval runs NBF steps -- the last one also evaluates knot N-1 for its pose cost (fpHelpers.cuh:235)
+    const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (EE || w < S.M - 1) ? NBF : NBF - 1;
+    float cacc = 0.f;                                          // EE: lane l < 7 carries s_cost[l]
     const float alpha = S.alpha[a], dt = S.dt;
     float *gx = S.x + ((size_t)b*S.A + a)*N*n, *gu = S.u + ((size_t)b*S.A + a)*N*m, *gdd = S.d + ((size_t)b*S.A + a)*N*n;
     float *gc = S.costk + ((size_t)b*S.A + a)*N;
@@ -637,7 +670,11 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
             s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
         }
         __syncwarp();
-        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
+        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
+        if (EE){
+            // running / final cost of this knot, not on the knots that close a defect (fpHelpers.cuh:259-265)
+            if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, s.u, k == N - 1, S)); }
+        }
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
         __syncwarp();
@@ -648,6 +685,14 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
             if (l < n && live){ gdd[((w+1)*NBF-1)*n + l] = SUB(s.xn[l], gx[(k+1)*n + l]); }
         }
         __syncwarp();
+    }
+    if (EE){
+        // cost partial of this (interval, candidate): s_cost[0] + ... + s_cost[6] in order (fpHelpers.cuh:299)
+        float J = __shfl_sync(FULL, cacc, 0, LANES);
+        #pragma unroll
+        for (int i = 1; i < kuka::NB; i++){ J = ADD(J, __shfl_sync(FULL, cacc, i, LANES)); }
+        if (l == 0 && live){ gc[w] = J; }
+        return;
     }
     // u[N-1] is never simulated and stays the accepted one
     if (w == S.M - 1 && live && l < m){ gu[(N-1)*m + l] = gup[(N-1)*m + l]; }
@@ -681,13 +726,18 @@ __global__ void select_kernel(DevState S, int mode, int b0){
     const int nA = (mode == 1) ? 1 : A;
     if (a < nA){
         float *v = ssel + (size_t)a*N; const float *gc = S.costk + ((size_t)b*A + a)*N;
-        for (int i = l; i < N; i += 32){ v[i] = ADD(0.f, gc[i]); }
-        __syncwarp();
-        for (int st = N/2; st >= 2; st >>= 1){
-            for (int i = l; i < st; i += 32){ v[i] = ADD(v[i], v[i+st]); }
+        if (S.ee && (mode == 0 || S.rolled_out)){
+            // costKern<T,0> (fpHelpers.cuh:165-172): the simulation's per-interval partials, summed in interval order
+            if (l == 0){ float J = 0.f; for (int i = 0; i < S.M; i++){ J = ADD(J, gc[i]); } sJ[a] = J; }
+        } else {
+            for (int i = l; i < N; i += 32){ v[i] = ADD(0.f, gc[i]); }
             __syncwarp();
+            for (int st = N/2; st >= 2; st >>= 1){
+                for (int i = l; i < st; i += 32){ v[i] = ADD(v[i], v[i+st]); }
+                __syncwarp();
+            }
+            if (l == 0){ sJ[a] = ADD(v[0], v[1]); }
         }
-        if (l == 0){ sJ[a] = ADD(v[0], v[1]); }
         // defect: max over the M-1 interval boundaries of the L1 norm (fpHelpers.cuh:94-111)
         float dmax = 0.f;
         if (mode == 0 && l < S.M - 1){
@@ -749,6 +799,7 @@ constexpr int NIS_LANES = 32;
 struct NisGroupSmem {
     kuka::FwdWs ws; kuka::GradWs gs;
     float x[16], u[8], qdd[8], dqdd[3*kuka::NB*kuka::NB + 1];
+    float ee[8], dee[6*kuka::NB + 2];      // tool pose and its derivative (EE_COST)
 };
 #ifndef PDDP_NIS_WARPS
 #define PDDP_NIS_WARPS 1
@@ -798,11 +849,13 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     const float *xg = S.xGoal + b*n;
     float *gg = S.g + ((size_t)b*N + k)*G_STRIDE;
     const bool fin = (k == N - 1);
+    if (!S.ee){
     for (int e = l; e < nm; e += LANES){
         if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
         else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
     }
-    if (write_H){
+    }
+    if (write_H && !S.ee){
         float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
         for (int e = l; e < nm*nm; e += LANES){
             const int i = e / nm, j = e % nm; float v = 0.f;
@@ -813,7 +866,47 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     }
     // integrator gradient AB = [I 0] + dt [0 I 0 ; dqdd]   (integrators.cuh:15-17,38-53); the final knot has none
     // (its group still runs the collective code so that both halves of a warp stay in lockstep, but stores nothing)
-    kuka::gradient<LANES>(s.ws, s.gs, sI, s.x, s.u, s.qdd, s.dqdd);
+    kuka::gradient<LANES>(s.ws, s.gs, sI, s.x, s.u, s.qdd, s.dqdd, S.ee ? s.ee : nullptr, S.ee ? s.dee : nullptr);
+    if (S.ee){
+        // costGrad with the pose terms (plants/cost_arm.cuh:328-388): g, and the whole Hessian at every knot -- Gauss-Newton on the
+        // pose (unweighted, as the reference has it) plus the diagonal weights
+        const float Rk = fin ? 0.f : S.R_EE;
+        for (int r = l; r < nm; r += LANES){
+            float val = 0.f;
+            if (r < np){
+                float v2 = 0.f;
+                #pragma unroll
+                for (int i = 0; i < 6; i++){
+                    const float dl = SUB(s.ee[i], xg[i]), Q = fin ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
+                    v2 = FMA(MUL(Q, dl), s.dee[r*6+i], v2);
+                }
+                val = ADD(val, v2);
+            }
+            if (r < n){ val = ADD(val, MUL((r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (fin ? S.QF_xdEE : S.Q_xdEE), s.x[r])); }   // the reference's build leaves this product unfused (pinned by its GPU unit dump)
+            else { val = FMA(Rk, s.u[r-n], val); }
+            gg[r] = val;
+        }
+        float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
+        for (int e = l; e < nm*nm; e += LANES){
+            const int cc = e / nm, r = e % nm; float val = 0.f;
+            if (r < np && cc < np){
+                #pragma unroll
+                for (int j = 0; j < 6; j++){ val = FMA(s.dee[r*6+j], s.dee[cc*6+j], val); }
+            }
+            if (r == cc){ val = ADD(val, (r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (r < n ? (fin ? S.QF_xdEE : S.Q_xdEE) : Rk)); }
+            gH[e] = val;
+        }
+        // initialisation without a rollout: the knot's cost (costGrad's d_JT, :383-388; single-valued costFunc :306-325)
+        if (mode == 1 && l == 0){
+            float cost = 0.f;
+            for (int ind = 0; ind < np; ind++){
+                if (ind == 0){ cost = ADD(cost, ee_pose_cost(s.ee, xg, fin, S)); }
+                cost = FMA(MUL(MUL(0.5f, Rk), s.u[ind]), s.u[ind], cost);
+                cost = ee_add_nominal(s.x, ind, fin, cost, S);
+            }
+            S.costk[((size_t)b*S.A + 0)*N + k] = cost;
+        }
+    }
     if (fin){ return; }
     float *gAB = S.AB + ((size_t)b*N + k)*AB_STRIDE;
     const float dt = S.dt;

@@ -54,6 +54,9 @@ extern "C" void pddp_default_config_kuka(pddp_config *c, int N, int batch){
     c->exp_red_min = (float)0.05; c->exp_red_max = (float)1.25; c->max_defect = (float)1.0; c->tol_cost = 0.0f;
     c->Q1 = (float)0.1; c->Q2 = (float)0.001; c->R = (float)0.0001; c->QF1 = (float)1000.0; c->QF2 = (float)1000.0;
     c->gravity = KUKA_GRAV;
+    c->ee_cost = 0;                                                    // plants/cost_arm.cuh:106-117 defaults
+    c->Q_EE1 = (float)0.1; c->Q_EE2 = 0.f; c->QF_EE1 = (float)1000.0; c->QF_EE2 = 0.f; c->R_EE = (float)0.0001;
+    c->Q_xdEE = (float)0.1; c->QF_xdEE = (float)1000.0; c->Q_xEE = 0.f; c->QF_xEE = 0.f;
 }
 
 extern "C" const char *pddp_last_error(pddp_handle h){ return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -101,6 +104,9 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.rho_min = cfg->rho_min; S.rho_max = cfg->rho_max; S.rho_factor = cfg->rho_factor; S.inv_rho_factor = (float)(1.0/(double)cfg->rho_factor);
     S.exp_red_min = cfg->exp_red_min; S.exp_red_max = cfg->exp_red_max; S.max_defect = cfg->max_defect;
     S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2; S.grav = cfg->gravity;
+    S.ee = cfg->ee_cost ? 1 : 0;
+    S.Q_EE1 = cfg->Q_EE1; S.Q_EE2 = cfg->Q_EE2; S.QF_EE1 = cfg->QF_EE1; S.QF_EE2 = cfg->QF_EE2; S.R_EE = cfg->R_EE;
+    S.Q_xdEE = cfg->Q_xdEE; S.QF_xdEE = cfg->QF_xdEE; S.Q_xEE = cfg->Q_xEE; S.QF_xEE = cfg->QF_xEE;
     float *dI, *dTb, *dal;
     #define DA(ptr, count, name) do { if (dalloc(h, &(ptr), (size_t)(count), name)){ return bail(PDDP_E_CUDA); } } while (0)
     DA(dI, 252, nullptr); DA(dTb, 252, nullptr); DA(dal, PDDP_MAX_ALPHA, nullptr);
@@ -137,7 +143,8 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
     CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
     CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
-    CKC(cudaFuncSetAttribute(sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
     CKC(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sel));
     CKC(cudaFuncSetAttribute(nis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nis));
     CKC(cudaFuncSetAttribute(unit_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_udyn));
@@ -202,13 +209,15 @@ static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInit
         // loadVarsGPU's forward rollout (nisInitHelpers.cuh:646-651): candidate 0 starts as the given trajectory and is simulated
         // with alpha[0], du = 0 and the feedback gains KT around it; the result (x, u, defects) becomes the start trajectory
         CK(cudaMemcpy2DAsync(S.x, (size_t)A*N*n*4, S.xp, (size_t)N*n*4, (size_t)N*n*4, B, cudaMemcpyDeviceToDevice, h->stream));
-        sim_kernel<<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1);
+        if (S.ee){ sim_kernel<true><<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1); }
+        else { sim_kernel<false><<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1); }
         h->launches += 1;
     }
     nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, rollout ? 2 : 1, 1, 0, S.B);
-    init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S);
+    // end-effector cost: the initial per-knot costs come from nis_kernel (they need the tool pose), or from the rollout's partials
+    if (!S.ee){ init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S); h->launches += 1; }
     select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1, 0);
-    h->launches += 3;
+    h->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -227,7 +236,8 @@ static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
 }
 static int launch_sim(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    sim_kernel<<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A);
+    if (S.ee){ sim_kernel<true><<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A); }
+    else { sim_kernel<false><<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A); }
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
@@ -361,6 +371,7 @@ __global__ void selftest_rcp_kernel(unsigned long long *bad){
 extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_init){
     if (!h){ return PDDP_E_INVALID; }
     if (!x_init || !u_init){ h->err = "null input"; return PDDP_E_INVALID; }
+    if (h->S.ee){ h->err = "the receding-horizon wrapper is built for the joint-space cost only (ee_cost = 0)"; return PDDP_E_INVALID; }
     DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m, A = S.A;
     CK(cudaSetDevice(h->cfg.device));
     if (!h->mpc.cx){

@@ -26,6 +26,8 @@ _DROP = re.compile(r"it\d+\.(nis|init)\.[xud]([1-9]|1\d)$")
 
 def run(N, *args):
     exe = os.path.join(REF, f"ref_mpc_N{N}" if args and args[0] == "mpc" else f"ref_driver_N{N}")
+    if args and str(args[0]).startswith("ee_"):          # end-effector cost build (EE_COST 1): oracle/ref_harness/ref_ee.cu
+        exe, args = os.path.join(REF, f"ref_ee_N{N}"), (args[0][3:],) + tuple(args[1:])
     print("+", exe, *args, flush=True)
     subprocess.run([exe, *[str(a) for a in args]], check=True, stdout=subprocess.DEVNULL)
 
@@ -43,7 +45,9 @@ def jobs(hw):
     out = [(32, ("unit", t, 64, 7), f"unit_{t}"),
            (32, ("trace", t, 0, 0.0, 2), f"trace_{t}_N32_s0_tol0"),
            (32, ("trace", t, 3, 0.0001, 1), f"trace_{t}_N32_s3_tol1e-4"),
-           (128, ("trace", t, 0, 0.0, 1), f"trace_{t}_N128_s0_tol0")]
+           (128, ("trace", t, 0, 0.0, 1), f"trace_{t}_N128_s0_tol0"),
+           # end-effector cost: cost / gradient / Hessian of costGradientHessianKern (G) / ...Threaded (H) on random states
+           (32, ("ee_unit", t, 64, 7), f"ee_unit_{t}")]
     if hw == "G":
         out += [(128, ("solve", "G", 0, 64, 0.0), "solve_G_N128_s0-63_tol0"),
                 (128, ("solve", "G", 0, 64, 0.0001), "solve_G_N128_s0-63_tol1e-4"),
@@ -53,7 +57,11 @@ def jobs(hw):
                 (128, ("warm", "G", 2, 0.0001, 0.0001), "warm_G_N128_s2"),
                 # receding horizon: runiLQR_MPC_GPU (MPC_MODE build, gravity 0): seed, steps, knots shifted per step, iteration cap
                 (32, ("mpc", 5, 8, 2, 4), "mpc_G_N32_s5"),
-                (128, ("mpc", 6, 5, 3, 6), "mpc_G_N128_s6")]
+                (128, ("mpc", 6, 5, 3, 6), "mpc_G_N128_s6"),
+                # end-effector cost: whole solves of the reference's EE_COST build
+                (32, ("ee_solve", "G", 0, 4, 0.0), "ee_solve_G_N32_s0-3_tol0"),
+                (128, ("ee_solve", "G", 0, 2, 0.0), "ee_solve_G_N128_s0-1_tol0"),
+                (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1")]
     return out
 
 

@@ -13,6 +13,9 @@ FP = C.POINTER(C.c_float)
 IP = C.POINTER(C.c_int)
 
 
+EE_WEIGHT_NAMES = ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")
+
+
 class Cfg(C.Structure):
     _fields_ = [("plant", C.c_int), ("n", C.c_int), ("m", C.c_int), ("npos", C.c_int), ("N", C.c_int),
                 ("n_alpha", C.c_int), ("M", C.c_int), ("integrator", C.c_int), ("max_iter", C.c_int),
@@ -20,7 +23,8 @@ class Cfg(C.Structure):
                 ("rho_init", F), ("rho_min", F), ("rho_max", F), ("rho_factor", F),
                 ("exp_red_min", F), ("exp_red_max", F), ("max_defect", F), ("tol_cost", F),
                 ("Q1", F), ("Q2", F), ("R", F), ("QF1", F), ("QF2", F),
-                ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float)]
+                ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float), ("ee_cost", C.c_int)] + \
+               [(k, F) for k in ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")]
 
 
 class Ws(C.Structure):
@@ -28,7 +32,7 @@ class Ws(C.Structure):
                                    "KT", "du", "ApBK", "Bdu", "xg")] + \
                [("J", F * MAX_ALPHA), ("dT", F * MAX_ALPHA), ("dJexp", F * 32), ("err", C.c_int * 16),
                 ("prevJ", F), ("dJ", F), ("z", F), ("rho", F), ("drho", F),
-                ("iter", C.c_int), ("alphaIndex", C.c_int), ("ignore_defect", C.c_int)]
+                ("iter", C.c_int), ("alphaIndex", C.c_int), ("ignore_defect", C.c_int), ("JTp", F * (MAX_ALPHA * 16))]
 
 
 def _build():
@@ -83,6 +87,9 @@ def lib(fma=False):
         getattr(L, _f).argtypes = [C.c_void_p]; getattr(L, _f).restype = FP
     L.orc_mpc_last_successful_solve.argtypes = [C.c_void_p]; L.orc_mpc_last_successful_solve.restype = C.c_int
     L.orc_solve_ex.argtypes = [cp, FP, FP, FP, FP, FP, FP, FP, C.c_int, C.c_int, C.c_int, FP, FP, FP, IP]; L.orc_solve_ex.restype = C.c_int
+    L.orc_ee_pos.argtypes = [cp, FP, FP, FP]
+    L.orc_ee_cost.argtypes = [cp, FP, FP, FP, FP, C.c_int]; L.orc_ee_cost.restype = F
+    L.orc_ee_cost_grad.argtypes = [cp, FP, FP, FP, FP, FP, FP, FP, C.c_int]
     L.orc_fma_mode.restype = C.c_int
     assert L.orc_fma_mode() == (1 if fma else 0)
     _libs[name] = L
@@ -96,7 +103,8 @@ def kuka_model():
     return z["I"].astype(np.float32), z["Tbody"].astype(np.float32)
 
 
-def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False):
+def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False, ee_weights=None):
+    """ee_weights: the nine end-effector cost weights (Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE) -> EE_COST 1"""
     L = lib(fma)
     c = Cfg()
     L.orc_default_cfg_kuka(C.byref(c), N)
@@ -104,6 +112,10 @@ def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False):
     c.I[:] = list(I); c.Tbody[:] = list(Tb)
     c.tol_cost = tol_cost
     c.expred_host_order = 1 if host_expred else 0
+    if ee_weights is not None:
+        c.ee_cost = 1
+        for k, v in zip(EE_WEIGHT_NAMES, ee_weights):
+            setattr(c, k, float(v))
     return c
 
 
