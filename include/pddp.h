@@ -91,6 +91,11 @@ int pddp_solve_device(pddp_handle h, const float *d_x0, const float *d_u0, const
  * each drawn from std::default_random_engine(seed) exactly as the deterministic harness does. HOST buffers. */
 int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal);
 
+/* EE_COST only: the reference's `xTarget` argument of costFunc / costGrad (plants/cost_arm.cuh:263-281) -- the nominal-state terms
+ * (Q_xEE, Q_xdEE) then measure x from it.  runiLQR_GPU passes none (the default here); runiLQR_MPC_GPU always passes its
+ * gv->d_xTarget (MPCHelpers.cuh:900), so a receding-horizon caller sets it.  HOST [batch][n]; NULL removes it. */
+int pddp_set_x_target(pddp_handle h, const float *xTarget);
+
 /* ---- plant plug-ins, evaluated on the device for n independent (x,u) samples (HOST buffers) -----------------------
  * dynamics (plants/dynamics_arm.cuh:2095), _integratorGradient (utils/integrators.cuh:38-53) */
 int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int n, float *qdd);

@@ -47,6 +47,8 @@ typedef struct {
     float gravity;               /* GRAVITY dynamics_arm.cuh:42-46 (9.81; 0 under MPC_MODE) */
     int   ee_cost;               /* EE_COST config.cuh:165-167: 1 = end-effector pose cost (goal = 6 floats), 0 = joint-space cost */
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;   /* cost_arm.cuh:106-117 */
+    int   use_xtarget;           /* EE_COST: the nominal-state terms measure x from xTarget (non-null on the receding-horizon path, MPCHelpers.cuh:900) */
+    float xTarget[ORC_MAX_N];
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */

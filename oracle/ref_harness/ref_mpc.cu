@@ -10,9 +10,26 @@
  * cost / step-size trace of the solve.
  *
  *   mpc <seed> <nsteps> <shift> <max_iter> <out.bin>
+ *
+ * Built twice (oracle/Makefile): ref_mpc_N* with the joint-space cost, ref_mpc_ee_N* with -DEE_COST=1 -- the configuration of
+ * examples/WAFR_MPC_examples.cu: end-effector pose goal, nominal-state terms measured from xTarget (always non-null on this
+ * path, MPCHelpers.cuh:889,900), roll/pitch/yaw weights set non-zero here so that the atan2 terms take part.
  */
 #define PLANT 4
+#ifndef EE_COST
 #define EE_COST 0
+#endif
+#if EE_COST
+#define _Q_EE1 0.1
+#define _Q_EE2 0.01
+#define _R_EE 0.0001
+#define _QF_EE1 1000.0
+#define _QF_EE2 10.0
+#define _Q_xdEE 0.1
+#define _QF_xdEE 1000.0
+#define _Q_xEE 0.001
+#define _QF_xEE 1.0
+#endif
 #define MPC_MODE 1
 #define USE_MAX_SOLVER_TIME 0
 #define USE_WAFR_URDF 1
@@ -56,7 +73,13 @@ int main(int argc, char **argv){
 	for (int k = 0; k < NT; k++){for (int i = 0; i < CONTROL_SIZE; i++){tv.u[k*md.ld_u+i] = static_cast<T>(0.01*(i+1));}}
 	memset(tv.KT, 0, md.ld_KT*DIM_KT_c*NT*sizeof(T));
 	const T goal[] = {0,0,0,-0.25*PI,0,0.25*PI,0.5*PI,0,0,0,0,0,0,0};
-	for (int i = 0; i < STATE_SIZE; i++){gv.xGoal[i] = goal[i]; gv.xTarget[i] = goal[i];}
+	#if EE_COST
+		const T pose[] = {(T)0.3638, (T)0.0, (T)1.0628, (T)(0.5*PI), (T)0.0, (T)(0.5*PI)};
+		for (int i = 0; i < 6; i++){gv.xGoal[i] = pose[i];}
+		for (int i = 0; i < STATE_SIZE; i++){gv.xTarget[i] = goal[i];}
+	#else
+		for (int i = 0; i < STATE_SIZE; i++){gv.xGoal[i] = goal[i]; gv.xTarget[i] = goal[i];}
+	#endif
 	// device state the wrapper expects to find: the plan in candidate slot alphaIndex = 0, everything else zero
 	gpuErrchk(cudaMemcpy(gv.h_d_x[0], tv.x, md.ld_x*NT*sizeof(T), cudaMemcpyHostToDevice));
 	gpuErrchk(cudaMemcpy(gv.h_d_u[0], tv.u, md.ld_u*NT*sizeof(T), cudaMemcpyHostToDevice));
@@ -76,7 +99,12 @@ int main(int argc, char **argv){
 	gpuErrchk(cudaMemset(gv.d_dT, 0, NUM_ALPHA*sizeof(T))); gpuErrchk(cudaMemset(gv.d_JT, 0, NUM_ALPHA*sizeof(T)));
 	gpuErrchk(cudaMemset(gv.d_dJexp, 0, 2*M_BLOCKS_B*sizeof(T)));
 	gpuErrchk(cudaDeviceSynchronize());
-	dumpf("x_init", tv.x, md.ld_x*NT); dumpf("u_init", tv.u, md.ld_u*NT); dumpf("xGoal", gv.xGoal, STATE_SIZE);
+	dumpf("x_init", tv.x, md.ld_x*NT); dumpf("u_init", tv.u, md.ld_u*NT); dumpf("xGoal", gv.xGoal, EE_COST ? 6 : STATE_SIZE);
+	#if EE_COST
+		dumpf("xTarget", gv.xTarget, STATE_SIZE);
+		{const float wts[9] = {(float)cst.Q_EE1, (float)cst.Q_EE2, (float)cst.QF_EE1, (float)cst.QF_EE2, (float)cst.R_EE, (float)cst.Q_xdEE, (float)cst.QF_xdEE, (float)cst.Q_xEE, (float)cst.QF_xEE};
+		 dumpf("weights", wts, 9);}
+	#endif
 	const double dt_us = TIME_STEP_LENGTH_IN_us;
 	int64_t t_plant = 1000000;      // arbitrary clock origin
 	std::vector<int> shifts, iters_per_step, lss;

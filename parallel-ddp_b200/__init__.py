@@ -44,7 +44,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged",
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target",
            "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -84,6 +84,7 @@ def load_library():
     L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
     L.pddp_mpc_init.argtypes = [H, FP, FP]
     L.pddp_set_skip_unchanged.argtypes = [H, C.c_int]
+    L.pddp_set_x_target.argtypes = [H, FP]
     L.pddp_traj_f_encoded_size.argtypes = [C.c_int, C.c_int, C.c_int]; L.pddp_traj_f_encoded_size.restype = C.c_long
     L.pddp_traj_f_encode.argtypes = [C.c_longlong, FP, C.c_int, FP, C.c_int, FP, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_encode.restype = C.c_long
     L.pddp_traj_f_decode.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_longlong), IP, IP, IP, FP, FP, FP, C.c_long, C.c_long, C.c_long]; L.pddp_traj_f_decode.restype = C.c_long
@@ -230,6 +231,13 @@ class Solver:
         rc = self.L.pddp_solve_device(self.h, d_x0, d_u0, d_xg, ignoreFirstDefectFlag, d_x, d_u, d_J, d_a, d_it,
                                       times.ctypes.data_as(DP) if times is not None else None)
         self._ck(rc, "pddp_solve_device")
+
+    def set_x_target(self, xTarget):
+        """EE_COST: xTarget [B,14] of the nominal-state cost terms (runiLQR_MPC_GPU's gv->xTarget), or None."""
+        if xTarget is None:
+            self._ck(self.L.pddp_set_x_target(self.h, None), "pddp_set_x_target"); return
+        a, pa = _f(np.broadcast_to(np.asarray(xTarget, np.float32).reshape(-1, 14), (self.cfg.batch, 14)))
+        self._ck(self.L.pddp_set_x_target(self.h, pa), "pddp_set_x_target")
 
     def set_skip_unchanged(self, on):
         """Opt-in: no gradient refresh for problems whose line search was rejected (results unchanged)."""

@@ -53,6 +53,8 @@ struct DevState {
     // end-effector cost (EE_COST 1, plants/cost_arm.cuh:204-389): xGoal[b][0..5] is the goal pose, costk[b][a][0..M-1] the
     // simulation's per-interval cost partials (fpHelpers.cuh:299)
     int ee;
+    int *init_knot;                // [B] EE_COST quirk of the receding-horizon path, see select_kernel mode 1 (0 everywhere else)
+    const float *xTarget;          // [B][n] or null: the nominal-state terms measure x from it (receding-horizon path, MPCHelpers.cuh:900)
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;
 };
 
@@ -587,17 +589,18 @@ __device__ __forceinline__ float ee_pose_cost(const float *ee, const float *goal
     return cost;
 }
 // `cost += nominalStateCost(...)` :263-270
-__device__ __forceinline__ float ee_add_nominal(const float *x, int ind, bool fin, float cost, const DevState &S){
-    const float Qq = fin ? S.QF_xEE : S.Q_xEE, Qqd = fin ? S.QF_xdEE : S.Q_xdEE, dq = x[ind], dqd = x[ind + kuka::NB];
+__device__ __forceinline__ float ee_add_nominal(const float *x, const float *xt, int ind, bool fin, float cost, const DevState &S){
+    const float Qq = fin ? S.QF_xEE : S.Q_xEE, Qqd = fin ? S.QF_xdEE : S.Q_xdEE;
+    const float dq = xt ? SUB(x[ind], xt[ind]) : x[ind], dqd = xt ? SUB(x[ind + kuka::NB], xt[ind + kuka::NB]) : x[ind + kuka::NB];
     return FMA(0.5f, FMA(MUL(Qq, dq), dq, MUL(MUL(Qqd, dqd), dqd)), cost);
 }
 // joint `ind`'s share of one knot (split costFunc :283-303)
-__device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *u, bool fin, const DevState &S){
+__device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *xt, const float *u, bool fin, const DevState &S){
     float cost = 0.f;
     if (ind == 0){ cost = ADD(cost, ee_pose_cost(ee, goal, fin, S)); }
     const float Rk = fin ? 0.f : S.R_EE;
     cost = FMA(MUL(MUL(0.5f, Rk), u[ind]), u[ind], cost);
-    return ee_add_nominal(x, ind, fin, cost, S);
+    return ee_add_nominal(x, xt, ind, fin, cost, S);
 }
 
 template <bool EE>
@@ -673,7 +676,7 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
         kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
         if (EE){
             // running / final cost of this knot, not on the knots that close a defect (fpHelpers.cuh:259-265)
-            if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, s.u, k == N - 1, S)); }
+            if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, S.xTarget ? S.xTarget + (size_t)b*n : nullptr, s.u, k == N - 1, S)); }
         }
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
@@ -752,6 +755,12 @@ __global__ void select_kernel(DevState S, int mode, int b0){
     if (threadIdx.x != 0){ return; }
     float *Jout = S.Jout + (size_t)b*(S.max_iter+1); int *alphaOut = S.alphaOut + (size_t)b*(S.max_iter+1);
     if (mode == 1){
+        // Reference behaviour under EE_COST: costGradientHessianKern leaves the per-knot costs in d_JT[0..N-1], costKern<T,1> puts
+        // their sum into d_JT[0] only, and initAlgGPU reads d_JT[*alphaIndex] (nisInitHelpers.cuh:388-391).  runiLQR_GPU starts with
+        // alphaIndex = 0; the receding-horizon wrapper keeps the previous solve's index, so when that is not 0 its "initial cost" is
+        // the cost of knot alphaIndex alone.  Reproduced as is (init_knot = that index, set by mpc_load_kernel).
+        const int ik = (S.ee && !S.rolled_out) ? S.init_knot[b] : 0;
+        if (ik != 0){ sJ[0] = S.costk[((size_t)b*A + 0)*N + ik]; }
         float pj = ADD(sJ[0], S.two_tol);                  // nisInitHelpers.cuh:393
         S.prevJ[b] = pj; Jout[0] = SUB(pj, S.two_tol); alphaOut[0] = S.rolled_out ? 0 : -1;     // nisInitHelpers.cuh:363
         return;
@@ -871,6 +880,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         // costGrad with the pose terms (plants/cost_arm.cuh:328-388): g, and the whole Hessian at every knot -- Gauss-Newton on the
         // pose (unweighted, as the reference has it) plus the diagonal weights
         const float Rk = fin ? 0.f : S.R_EE;
+        const float *xt = S.xTarget ? S.xTarget + (size_t)b*n : nullptr;
         for (int r = l; r < nm; r += LANES){
             float val = 0.f;
             if (r < np){
@@ -882,7 +892,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
                 }
                 val = ADD(val, v2);
             }
-            if (r < n){ val = ADD(val, MUL((r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (fin ? S.QF_xdEE : S.Q_xdEE), s.x[r])); }   // the reference's build leaves this product unfused (pinned by its GPU unit dump)
+            if (r < n){ val = ADD(val, MUL((r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (fin ? S.QF_xdEE : S.Q_xdEE), xt ? SUB(s.x[r], xt[r]) : s.x[r])); }   // the reference's build leaves this product unfused (pinned by its GPU unit dump)
             else { val = FMA(Rk, s.u[r-n], val); }
             gg[r] = val;
         }
@@ -902,7 +912,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
             for (int ind = 0; ind < np; ind++){
                 if (ind == 0){ cost = ADD(cost, ee_pose_cost(s.ee, xg, fin, S)); }
                 cost = FMA(MUL(MUL(0.5f, Rk), s.u[ind]), s.u[ind], cost);
-                cost = ee_add_nominal(s.x, ind, fin, cost, S);
+                cost = ee_add_nominal(s.x, xt, ind, fin, cost, S);
             }
             S.costk[((size_t)b*S.A + 0)*N + k] = cost;
         }
@@ -957,6 +967,7 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q, int cur){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, LANES = 32;          // the rollout is one trajectory: the whole warp works on it
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b]; const bool clear = Q.clear[b] != 0;
+    if (threadIdx.x == 0){ S.init_knot[b] = S.ee ? S.alphaIndex[b] : 0; }      // the slot index the reference's plan lives in (the reset that follows zeroes alphaIndex)
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
     float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     float *P0 = S.Pbuf[0] + (size_t)b*N*n*n, *P1 = S.Pbuf[1] + (size_t)b*N*n*n, *p0 = S.pbuf[0] + (size_t)b*N*n, *p1 = S.pbuf[1] + (size_t)b*N*n;

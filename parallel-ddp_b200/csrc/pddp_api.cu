@@ -41,6 +41,7 @@ struct pddp_solver {
     cudaEvent_t ev[8];
     double last_ms = 0; int last_launches = 0;
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
+    float *d_xTarget = nullptr;
     std::map<std::string, std::pair<void*, size_t>> arrays;
 };
 
@@ -124,6 +125,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     DA(S.xGoal, (size_t)B*n, "xGoal"); DA(S.costk, (size_t)B*A*N, "costk");
     DA(S.J, (size_t)B*A, "J"); DA(S.dT, (size_t)B*A, "dT"); DA(S.dJexp, (size_t)B*2*M, "dJexp");
     DA(S.rho, B, "rho"); DA(S.drho, B, "drho"); DA(S.prevJ, B, "prevJ"); DA(S.dJ, B, "dJ"); DA(S.z, B, "z");
+    DA(S.init_knot, B, nullptr);
     DA(S.iter, B, "iter"); DA(S.alphaIndex, B, "alphaIndex"); DA(S.ignore_defect, B, "ignore_defect"); DA(S.done, B, "done");
     DA(S.accepted, B, "accepted"); DA(S.final_src, B, "final_src");
     DA(S.Jout, (size_t)B*(cfg->max_iter+1), "Jout"); DA(S.alphaOut, (size_t)B*(cfg->max_iter+1), "alphaOut");
@@ -179,6 +181,7 @@ __global__ void reset_kernel(DevState S, float rho_init, int ignore_first){
 
 static int launch_reset(pddp_handle h, int ignore_first, int clear){
     DevState &S = h->S; const int B = S.B, N = S.N, A = S.A, n = S.n, m = S.m;
+    CK(cudaMemsetAsync(S.init_knot, 0, (size_t)B*sizeof(int), h->stream));       // runiLQR_GPU starts from alphaIndex = 0
     if (clear){
         // loadVarsGPU with clearVarsFlag=1 (nisInitHelpers.cuh:612-620)
         CK(cudaMemsetAsync(S.Pbuf[0], 0, (size_t)B*N*n*n*4, h->stream)); CK(cudaMemsetAsync(S.Pbuf[1], 0, (size_t)B*N*n*n*4, h->stream));
@@ -368,10 +371,22 @@ __global__ void selftest_rcp_kernel(unsigned long long *bad){
 }
 }
 // ---------------------------------------------------------------------------------------------------- receding horizon
+// EE_COST: the reference's xTarget argument (costFunc / costGrad cost_arm.cuh:263-281; null for runiLQR_GPU, gv->d_xTarget for
+// runiLQR_MPC_GPU, MPCHelpers.cuh:900).  HOST [batch][n], or NULL for "no target".
+extern "C" int pddp_set_x_target(pddp_handle h, const float *xTarget){
+    if (!h){ return PDDP_E_INVALID; }
+    DevState &S = h->S; const size_t B = S.B, n = S.n;
+    CK(cudaSetDevice(h->cfg.device));
+    if (!xTarget){ S.xTarget = nullptr; return 0; }
+    if (!h->d_xTarget){ void *q = nullptr; CK(cudaMalloc(&q, B*n*4)); h->d_xTarget = (float*)q; h->allocs.push_back(q); }
+    CK(cudaMemcpy(h->d_xTarget, xTarget, B*n*4, cudaMemcpyHostToDevice));
+    S.xTarget = h->d_xTarget;
+    return 0;
+}
+
 extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_init){
     if (!h){ return PDDP_E_INVALID; }
     if (!x_init || !u_init){ h->err = "null input"; return PDDP_E_INVALID; }
-    if (h->S.ee){ h->err = "the receding-horizon wrapper is built for the joint-space cost only (ee_cost = 0)"; return PDDP_E_INVALID; }
     DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, m = S.m, A = S.A;
     CK(cudaSetDevice(h->cfg.device));
     if (!h->mpc.cx){
@@ -396,6 +411,7 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
     CK(cudaMemsetAsync(S.pbuf[0], 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(S.pbuf[1], 0, B*N*n*4, h->stream));
     CK(cudaMemsetAsync(h->mpc.x_old, 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(h->mpc.u_old, 0, B*N*m*4, h->stream)); CK(cudaMemsetAsync(h->mpc.KT_old, 0, B*N*n*m*4, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemset(S.alphaIndex, 0, B*sizeof(int)));                 // the plan starts in slot 0 (MPCHelpers.cuh:236)
     h->mpc_lss.assign(B, 0); h->mpc_ready = true; h->cur = 0;
     return 0;
 }

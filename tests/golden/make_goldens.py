@@ -26,6 +26,8 @@ _DROP = re.compile(r"it\d+\.(nis|init)\.[xud]([1-9]|1\d)$")
 
 def run(N, *args):
     exe = os.path.join(REF, f"ref_mpc_N{N}" if args and args[0] == "mpc" else f"ref_driver_N{N}")
+    if args and args[0] == "mpc_ee":                    # receding horizon built with EE_COST 1 (ref_mpc.cu -DEE_COST=1)
+        exe, args = os.path.join(REF, f"ref_mpc_ee_N{N}"), ("mpc",) + tuple(args[1:])
     if args and str(args[0]).startswith("ee_"):          # end-effector cost build (EE_COST 1): oracle/ref_harness/ref_ee.cu
         exe, args = os.path.join(REF, f"ref_ee_N{N}"), (args[0][3:],) + tuple(args[1:])
     print("+", exe, *args, flush=True)
@@ -61,7 +63,8 @@ def jobs(hw):
                 # end-effector cost: whole solves of the reference's EE_COST build
                 (32, ("ee_solve", "G", 0, 4, 0.0), "ee_solve_G_N32_s0-3_tol0"),
                 (128, ("ee_solve", "G", 0, 2, 0.0), "ee_solve_G_N128_s0-1_tol0"),
-                (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1")]
+                (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1"),
+                (32, ("mpc_ee", 5, 8, 2, 4), "mpc_ee_G_N32_s5")]
     return out
 
 

@@ -24,7 +24,8 @@ class Cfg(C.Structure):
                 ("exp_red_min", F), ("exp_red_max", F), ("max_defect", F), ("tol_cost", F),
                 ("Q1", F), ("Q2", F), ("R", F), ("QF1", F), ("QF2", F),
                 ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float), ("ee_cost", C.c_int)] + \
-               [(k, F) for k in ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")]
+               [(k, F) for k in ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")] + \
+               [("use_xtarget", C.c_int), ("xTarget", F * 16)]
 
 
 class Ws(C.Structure):
@@ -103,7 +104,7 @@ def kuka_model():
     return z["I"].astype(np.float32), z["Tbody"].astype(np.float32)
 
 
-def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False, ee_weights=None):
+def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False, ee_weights=None, x_target=None):
     """ee_weights: the nine end-effector cost weights (Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE) -> EE_COST 1"""
     L = lib(fma)
     c = Cfg()
@@ -116,6 +117,9 @@ def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False, ee_weights=None):
         c.ee_cost = 1
         for k, v in zip(EE_WEIGHT_NAMES, ee_weights):
             setattr(c, k, float(v))
+    if x_target is not None:
+        c.use_xtarget = 1
+        c.xTarget[:14] = [float(v) for v in x_target]
     return c
 
 

@@ -3,6 +3,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python tests/golden/make_goldens.py gpu ee_ 2>&1 | tail -5
+timeout 300 python tests/golden/make_goldens.py gpu mpc_ee 2>&1 | tail -2
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
 PDDP_GROUPS=1 python tools/prof_run.py 20 64 2>&1 | tail -1
 PDDP_EE=1 PDDP_GROUPS=1 python tools/prof_run.py 20 64 2>&1 | tail -1
