@@ -96,6 +96,19 @@ int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0
  * gv->d_xTarget (MPCHelpers.cuh:900), so a receding-horizon caller sets it.  HOST [batch][n]; NULL removes it. */
 int pddp_set_x_target(pddp_handle h, const float *xTarget);
 
+/* Consumer side of the hand-off: replaces getHardwareControls (DDPHelpers/MPCHelpers.cuh:817-858), the host function that turns
+ * the published plan and a measured state into the joint command.  Zero-order hold on u and KT, first-order hold on x:
+ *   steps = (tActual - t0) / (time_step * 1e6)   [times in microseconds, time_step = TOTAL_TIME/(N-1) in seconds]
+ *   k = (int)steps, f = steps - k;  returns 1 (and writes nothing) when k >= N-2 or k < 0
+ *   u_out = u[k] - K[k] (xActual - ((1-f) x[k] + f x[k+1]))          (float arithmetic, as the reference's T)
+ *   q_out = qActual (PD_GAINS_ON_STATE 0, the reference's default) or the interpolated plan position (pd_gains_on_state != 0)
+ *   use_feedback = 0 (USE_FEEDBACK_IN_TRAJ_RUNNER 0): u_out = u[k]
+ *   alpha > 0 with u_prev != NULL: u_out = (1-alpha) u_out + alpha u_prev, u_prev = u_out          (double arithmetic)
+ * x [N][14], u [N][7], KT [N][14*7] in the reference layouts; qActual, qdActual, q_out, u_out, u_prev: 7 doubles.  HOST only. */
+int pddp_hardware_controls(int N, double time_step, const float *x, const float *u, const float *KT, double t0,
+                           const double *qActual, const double *qdActual, double tActual, int use_feedback, int pd_gains_on_state,
+                           double *u_prev, double alpha, double *q_out, double *u_out);
+
 /* ---- plant plug-ins, evaluated on the device for n independent (x,u) samples (HOST buffers) -----------------------
  * dynamics (plants/dynamics_arm.cuh:2095), _integratorGradient (utils/integrators.cuh:38-53) */
 int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int n, float *qdd);

@@ -45,7 +45,7 @@ EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
            "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target",
-           "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
+           "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
 FP = C.POINTER(C.c_float)
@@ -85,6 +85,7 @@ def load_library():
     L.pddp_mpc_init.argtypes = [H, FP, FP]
     L.pddp_set_skip_unchanged.argtypes = [H, C.c_int]
     L.pddp_set_x_target.argtypes = [H, FP]
+    L.pddp_hardware_controls.argtypes = [C.c_int, C.c_double, FP, FP, FP, C.c_double, DP, DP, C.c_double, C.c_int, C.c_int, DP, C.c_double, DP, DP]
     L.pddp_traj_f_encoded_size.argtypes = [C.c_int, C.c_int, C.c_int]; L.pddp_traj_f_encoded_size.restype = C.c_long
     L.pddp_traj_f_encode.argtypes = [C.c_longlong, FP, C.c_int, FP, C.c_int, FP, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_encode.restype = C.c_long
     L.pddp_traj_f_decode.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_longlong), IP, IP, IP, FP, FP, FP, C.c_long, C.c_long, C.c_long]; L.pddp_traj_f_decode.restype = C.c_long
@@ -314,3 +315,17 @@ class Solver:
             self.freeMemory_GPU()
         except Exception:
             pass
+
+
+def hardware_controls(x, u, KT, t0, qActual, qdActual, tActual, time_step, use_feedback=True, pd_gains_on_state=False, u_prev=None, alpha=0.0):
+    """getHardwareControls (MPCHelpers.cuh:817-858): joint command from the published plan x [N,14], u [N,7], KT [N,98] and the
+    measured state at time tActual (microseconds, like t0).  Returns (err, q_out[7], u_out[7]); err = 1 when tActual is beyond
+    the plan.  u_prev (float64[7], updated in place) with alpha > 0 turns on the reference's exponential smoothing."""
+    L = load_library()
+    x, px = _f(x); u, pu = _f(u); KT, pk = _f(KT)
+    qa = np.ascontiguousarray(qActual, np.float64); qda = np.ascontiguousarray(qdActual, np.float64)
+    qo = np.zeros(7, np.float64); uo = np.zeros(7, np.float64)
+    pp = u_prev.ctypes.data_as(DP) if u_prev is not None else None
+    err = L.pddp_hardware_controls(x.size // 14, float(time_step), px, pu, pk, float(t0), qa.ctypes.data_as(DP), qda.ctypes.data_as(DP), float(tActual),
+                                   int(use_feedback), int(pd_gains_on_state), pp, float(alpha), qo.ctypes.data_as(DP), uo.ctypes.data_as(DP))
+    return err, qo, uo

@@ -480,6 +480,40 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------- consumer side of the hand-off
+// getHardwareControls (MPCHelpers.cuh:817-858): host arithmetic in the reference (float products and sums rounded one by one, the
+// smoothing in double), restated operation by operation.
+extern "C" int pddp_hardware_controls(int N, double time_step, const float *x, const float *u, const float *KT, double t0,
+                                      const double *qActual, const double *qdActual, double tActual, int use_feedback, int pd_gains_on_state,
+                                      double *u_prev, double alpha, double *q_out, double *u_out){
+    constexpr int n = kuka::NX, m = kuka::NU, np = kuka::NB;
+    if (N < 3 || !x || !u || !KT || !qActual || !qdActual || !q_out || !u_out){ return PDDP_E_INVALID; }
+    const double step_us = (time_step*1000.0)*1000.0;                       // TIME_STEP_LENGTH_IN_us, :29-30
+    const double dt = (tActual - t0)/step_us; const int k = static_cast<int>(dt); const double fraction = dt - static_cast<double>(k);
+    if (k >= N - 2 || k < 0){ return 1; }                                   // beyond the plan (:827)
+    const float *uk = u + (size_t)k*m;
+    if (use_feedback){
+        const float *KTk = KT + (size_t)k*n*m, *xd = x + (size_t)k*n, *xu = x + (size_t)(k+1)*n;
+        volatile float dx[n];                                               // volatile: every float operation is rounded on its own (no contraction by the host compiler)
+        const float w0 = static_cast<float>(1.0 - fraction), w1 = static_cast<float>(fraction);
+        for (int i = 0; i < n; i++){
+            volatile float a = w0*xd[i], b = w1*xu[i]; volatile float val = a + b;
+            dx[i] = static_cast<float>(i < np ? qActual[i] : qdActual[i-np]) - val;
+            if (pd_gains_on_state && i < np){ q_out[i] = static_cast<double>(val); }
+        }
+        for (int r = 0; r < m; r++){
+            volatile float val = uk[r];
+            for (int c = 0; c < n; c++){ volatile float p = KTk[c + r*n]*dx[c]; val = val - p; }
+            u_out[r] = static_cast<double>(val);
+        }
+    } else {
+        for (int i = 0; i < m; i++){ u_out[i] = static_cast<double>(uk[i]); }
+    }
+    if (!pd_gains_on_state){ for (int i = 0; i < np; i++){ q_out[i] = qActual[i]; } }
+    if (u_prev && alpha > 0){ for (int i = 0; i < m; i++){ u_out[i] = (1 - alpha)*u_out[i] + alpha*u_prev[i]; u_prev[i] = u_out[i]; } }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- trajectory hand-off
 // lcmt_trajectory_f (lcmtypes/drake/lcmt_trajectory_f.hpp): LCM wire format = 8-byte fingerprint, then the fields in declaration
 // order, every scalar in network byte order.  Host-only code.

@@ -80,6 +80,8 @@ def main():
         for fb in (1, 0):
             out = os.path.join(HERE, f"lcm_traj_f_N8_{'fb' if fb else 'nofb'}.bin")
             subprocess.run([os.path.join(REF, "ref_lcm_traj"), "8", str(fb), out], check=True, stdout=subprocess.DEVNULL)
+        # consumer side of the hand-off: getHardwareControls on a random plan (host code of the reference)
+        b = os.path.join(tmp, "hwc.bin"); subprocess.run([os.path.join(REF, "ref_hwc"), "3", b], check=True); to_npz(b, os.path.join(HERE, "hwc_N32_s3.npz"))
         d = refdump.load(os.path.join(tmp, "unit_H.bin"))
         np.savez(os.path.join(HERE, "kuka_model.npz"), I=d["I"], Tbody=d["Tbody"])
     elif mode == "gpu":

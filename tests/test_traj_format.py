@@ -62,3 +62,24 @@ def test_encode_decode_round_trip_and_errors():
         if need > 28:
             with pytest.raises(pddp.PddpError):
                 pddp.traj_f_decode(bytes(buf)[:-1])                                                   # truncated
+
+
+def test_hardware_controls_vs_reference(golden_dir):
+    """Consumer side of the hand-off: getHardwareControls (MPCHelpers.cuh:817-858) of the unmodified reference
+    (oracle/ref_harness/ref_hwc.cu) on a random plan -- inside the plan, on knot boundaries, before its start (the reference
+    truncates toward zero and extrapolates), past its end (error return), with and without the exponential smoothing."""
+    d = dict(np.load(os.path.join(golden_dir, "hwc_N32_s3.npz")))
+    N, nt = int(d["meta"][0]), int(d["meta"][1]); t0, time_step = float(d["consts"][0]), float(d["consts"][1])
+    x = d["x"].reshape(N, 14); u = d["u"].reshape(N, 7); KT = d["KT"].reshape(N, 98)
+    u_prev = np.zeros(7, np.float64)
+    for i in range(nt):
+        al = float(d["alpha"][i])
+        err, qo, uo = pddp.hardware_controls(x, u, KT, t0, d["qActual"].reshape(nt, 7)[i], d["qdActual"].reshape(nt, 7)[i], float(d["tActual"][i]), time_step,
+                                             u_prev=u_prev if al > 0 else None, alpha=al)
+        assert err == int(d["err"][i]), i
+        if err == 0:
+            assert np.array_equal(uo, d["u_out"].reshape(nt, 7)[i]), (i, uo, d["u_out"].reshape(nt, 7)[i])
+            assert np.array_equal(qo, d["q_out"].reshape(nt, 7)[i]), i
+    # without feedback the command is the plan's control of the current knot
+    err, qo, uo = pddp.hardware_controls(x, u, KT, t0, np.zeros(7), np.zeros(7), t0 + 2.5 * time_step * 1e6, time_step, use_feedback=False)
+    assert err == 0 and np.array_equal(uo, u[2].astype(np.float64))
