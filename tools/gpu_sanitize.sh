@@ -1,5 +1,6 @@
 #!/bin/bash
-# compute-sanitizer over one small solve (N=32, 2 problems, 3 iterations), a warm start and two receding-horizon steps
+# compute-sanitizer over one small solve (N=32, 2 problems, 3 iterations), a warm start and two receding-horizon steps, with the
+# joint-space cost and with the end-effector cost (xTarget set)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 cat > /tmp/san.py <<'PY'
@@ -16,6 +17,17 @@ s.mpc_init(x0, u0 * 0 + 0.01)
 for st in range(2):
     s.mpc_step(s.mpc_x[:, 0].copy(), xg, 0 if st == 0 else 2, 2, clear_vars=1 if st == 0 else 0)
 print("done", o["iters"], o2["iters"])
+# end-effector cost: cold solve, rollout start, receding horizon with xTarget
+xe = np.zeros((B, 14), np.float32); xe[:, :6] = (0.3638, 0.0, 1.0628, 1.570795, 0.0, 1.570795)
+w = dict(zip(pddp.EE_WEIGHT_NAMES, (0.1, 0.01, 1000.0, 10.0, 1e-4, 0.1, 1000.0, 1e-3, 1.0)))
+e = pddp.Solver(pddp.default_config_kuka(N, B, max_iter=3, ee_cost=1, gravity=0.0, **w))
+oe = e.runiLQR_GPU(x0, u0, xe)
+oe2 = e.runiLQR_GPU(oe["x"], oe["u"], xe, forwardRolloutFlag=1, clearVarsFlag=0, KT0=z(B, N, 98), P0=z(B, N, 196), p0=z(B, N, 14), d0=z(B, N, 14))
+e.set_x_target(xg)
+e.mpc_init(x0, u0 * 0 + 0.01)
+for st in range(3):
+    e.mpc_step(e.mpc_x[:, 0].copy(), xe, 0 if st == 0 else 2, 2, clear_vars=1 if st == 0 else 0)
+print("done ee", oe["iters"], oe2["iters"])
 PY
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"; timeout 500 compute-sanitizer --tool $tool python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done|Error|hazard" | head -8
