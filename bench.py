@@ -39,6 +39,11 @@ CONFIG = {"workload": f"configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batc
           "max_iter": MAX_ITER, "l2": f"a 256 MiB buffer is rewritten between timed steps (working set {1.08*BATCH_PER_GPU:.0f} MB)",
           # every iteration does the reference's full work (rejected line searches included) unless PDDP_SKIP_UNCHANGED=1 is set
           "skip_unchanged_gradient_refresh": bool(int(os.environ.get("PDDP_SKIP_UNCHANGED", "0") or 0))}
+# secondary data point (not the headline): the same shape under the reference's end-effector cost (EE_COST 1, default weights, the
+# goal pose of WAFR_iLQR_examples.cu:37-43); the reference arm and the CPU baseline stay on the joint-space cost
+BENCH_EE = bool(int(os.environ.get("PDDP_BENCH_EE", "0") or 0))
+if BENCH_EE:
+    CONFIG["workload"] += " -- end-effector cost (EE_COST 1)"; CONFIG["cost"] = "end_effector"
 
 
 def peaks():
@@ -164,12 +169,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pddp = importlib.import_module("parallel-ddp_b200")
     B, N, L1 = BATCH_PER_GPU, N_KNOTS, MAX_ITER + 1
-    cfg = pddp.default_config_kuka(N, B, device=local_rank, tol_cost=0.0)
+    cfg = pddp.default_config_kuka(N, B, device=local_rank, tol_cost=0.0, ee_cost=1 if BENCH_EE else 0)
     solver = pddp.Solver(cfg)
     # this rank's shard of the global batch (seed = problem index): problems lo .. hi-1
     sharding = importlib.import_module("parallel-ddp_b200.sharding")
     lo, hi = sharding.shard_range(rank, world, B * world)
     x0, u0, xg = pddp.make_inputs_kuka(N, hi - lo, seed0=lo)
+    if BENCH_EE:
+        xg[:] = 0; xg[:, :6] = (0.3638, 0.0, 1.0628, 0.5 * 3.14159, 0.0, 0.5 * 3.14159)
     dev = torch.device("cuda", local_rank)
     d_x0 = torch.from_numpy(x0).to(dev); d_u0 = torch.from_numpy(u0).to(dev); d_xg = torch.from_numpy(xg).to(dev)
     d_x = torch.empty_like(d_x0); d_u = torch.empty_like(d_u0)
