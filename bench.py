@@ -114,7 +114,7 @@ def oracle_port_run(nprob):
     return tot / dt, tot, dt, 1
 
 
-def cpu_baseline(nseeds=8):
+def cpu_baseline(nseeds=16):      # about 11 s of host work on the GPU box (16 threads)
     r = ref_cpu_run(nseeds)
     if r:
         return {"value": r[0], "unit": UNIT, "cores": r[3], "kind": "reference",
