@@ -91,6 +91,11 @@ int pddp_solve_device(pddp_handle h, const float *d_x0, const float *d_u0, const
  * each drawn from std::default_random_engine(seed) exactly as the deterministic harness does. HOST buffers. */
 int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal);
 
+/* runiLQR_MPC_GPU's `use_cost_shift` argument (MPCHelpers.cuh:866,876): when on, every pddp_mpc_step evaluates the pose terms of the
+ * end-effector cost with their final weights from knot N-1-shiftAmount on (finalCostShift = shiftAmount).  Ignored by the
+ * joint-space cost, as in the reference. */
+int pddp_mpc_set_cost_shift(pddp_handle h, int use_cost_shift);
+
 /* EE_COST only: the reference's `xTarget` argument of costFunc / costGrad (plants/cost_arm.cuh:263-281) -- the nominal-state terms
  * (Q_xEE, Q_xdEE) then measure x from it.  runiLQR_GPU passes none (the default here); runiLQR_MPC_GPU always passes its
  * gv->d_xTarget (MPCHelpers.cuh:900), so a receding-horizon caller sets it.  HOST [batch][n]; NULL removes it. */

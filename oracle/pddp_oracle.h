@@ -49,6 +49,7 @@ typedef struct {
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;   /* cost_arm.cuh:106-117 */
     int   use_xtarget;           /* EE_COST: the nominal-state terms measure x from xTarget (non-null on the receding-horizon path, MPCHelpers.cuh:900) */
     float xTarget[ORC_MAX_N];
+    int   final_cost_shift;      /* EE_COST: finalCostShift of runiLQR_MPC_GPU (MPCHelpers.cuh:876): the pose terms take their final weights from knot N-1-shift on */
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */

@@ -9,7 +9,7 @@
  * fixed perturbation.  After every step it dumps the published trajectory (trajVars x, u, KT), the failure counter and the
  * cost / step-size trace of the solve.
  *
- *   mpc <seed> <nsteps> <shift> <max_iter> <out.bin>
+ *   mpc <seed> <nsteps> <shift> <max_iter> <out.bin> [use_cost_shift]
  *
  * Built twice (oracle/Makefile): ref_mpc_N* with the joint-space cost, ref_mpc_ee_N* with -DEE_COST=1 -- the configuration of
  * examples/WAFR_MPC_examples.cu: end-effector pose goal, nominal-state terms measured from xTarget (always non-null on this
@@ -57,7 +57,8 @@ static void dumpi(const std::string &name, const int *p, size_t n){ dumpraw(name
 static std::string nm(const char *base, int s){ char b[64]; snprintf(b, sizeof b, "s%d.%s", s, base); return b; }
 
 int main(int argc, char **argv){
-	if (argc != 7 || std::string(argv[1]) != "mpc"){fprintf(stderr, "usage: ref_mpc mpc <seed> <nsteps> <shift> <max_iter> <out.bin>\n"); return 2;}
+	if ((argc != 7 && argc != 8) || std::string(argv[1]) != "mpc"){fprintf(stderr, "usage: ref_mpc mpc <seed> <nsteps> <shift> <max_iter> <out.bin> [use_cost_shift]\n"); return 2;}
+	const bool use_cost_shift = argc == 8 && atoi(argv[7]) != 0;      // runiLQR_MPC_GPU's last argument: final pose weights on the last shift+1 knots (MPCHelpers.cuh:876)
 	const unsigned seed = (unsigned)atoi(argv[2]); const int nsteps = atoi(argv[3]), shift = atoi(argv[4]), max_iter = atoi(argv[5]);
 	g_out = fopen(argv[6], "wb"); if (!g_out){perror("open"); return 1;}
 	trajVars<T> tv; GPUVars<T> gv; matDimms md; algTrace<T> data; costParams<T> cst;
@@ -121,13 +122,13 @@ int main(int argc, char **argv){
 		}
 		dumpf(nm("xActual", s), gv.xActual, STATE_SIZE);
 		const size_t j0 = data.J.size();
-		runiLQR_MPC_GPU<T>(&tv, &gv, &md, &data, &cst, t_plant, t_plant, 0, max_iter, 1e12, s == 0 ? 1 : 0, 0);
+		runiLQR_MPC_GPU<T>(&tv, &gv, &md, &data, &cst, t_plant, t_plant, 0, max_iter, 1e12, s == 0 ? 1 : 0, use_cost_shift);
 		std::vector<float> J(data.J.begin() + j0, data.J.end()); std::vector<int> al(data.alpha.begin() + j0, data.alpha.end());
 		dumpf(nm("Jout", s), J.data(), J.size()); dumpi(nm("alphaOut", s), al.data(), al.size());
 		dumpf(nm("x", s), tv.x, md.ld_x*NT); dumpf(nm("u", s), tv.u, md.ld_u*NT); dumpf(nm("KT", s), tv.KT, md.ld_KT*DIM_KT_c*NT);
 		shifts.push_back(expect_shift); iters_per_step.push_back((int)J.size() - 1); lss.push_back(tv.last_successful_solve);
 	}
-	int meta[6] = {NT, NUM_ALPHA, M_BLOCKS, nsteps, shift, max_iter}; dumpi("meta", meta, 6);
+	int meta[7] = {NT, NUM_ALPHA, M_BLOCKS, nsteps, shift, max_iter, use_cost_shift ? 1 : 0}; dumpi("meta", meta, 7);
 	dumpi("shifts", shifts.data(), shifts.size()); dumpi("iters", iters_per_step.data(), iters_per_step.size()); dumpi("last_successful_solve", lss.data(), lss.size());
 	fclose(g_out);
 	return 0;

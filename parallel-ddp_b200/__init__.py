@@ -44,7 +44,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target",
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     L.pddp_mpc_init.argtypes = [H, FP, FP]
     L.pddp_set_skip_unchanged.argtypes = [H, C.c_int]
     L.pddp_set_x_target.argtypes = [H, FP]
+    L.pddp_mpc_set_cost_shift.argtypes = [H, C.c_int]
     L.pddp_hardware_controls.argtypes = [C.c_int, C.c_double, FP, FP, FP, C.c_double, DP, DP, C.c_double, C.c_int, C.c_int, DP, C.c_double, DP, DP]
     L.pddp_traj_f_encoded_size.argtypes = [C.c_int, C.c_int, C.c_int]; L.pddp_traj_f_encoded_size.restype = C.c_long
     L.pddp_traj_f_encode.argtypes = [C.c_longlong, FP, C.c_int, FP, C.c_int, FP, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_encode.restype = C.c_long
@@ -239,6 +240,10 @@ class Solver:
             self._ck(self.L.pddp_set_x_target(self.h, None), "pddp_set_x_target"); return
         a, pa = _f(np.broadcast_to(np.asarray(xTarget, np.float32).reshape(-1, 14), (self.cfg.batch, 14)))
         self._ck(self.L.pddp_set_x_target(self.h, pa), "pddp_set_x_target")
+
+    def mpc_set_cost_shift(self, on):
+        """runiLQR_MPC_GPU's use_cost_shift: final pose weights on the last shiftAmount+1 knots of every receding-horizon step (EE_COST)."""
+        self._ck(self.L.pddp_mpc_set_cost_shift(self.h, int(on)), "pddp_mpc_set_cost_shift")
 
     def set_skip_unchanged(self, on):
         """Opt-in: no gradient refresh for problems whose line search was rejected (results unchanged)."""

@@ -53,6 +53,7 @@ struct DevState {
     // end-effector cost (EE_COST 1, plants/cost_arm.cuh:204-389): xGoal[b][0..5] is the goal pose, costk[b][a][0..M-1] the
     // simulation's per-interval cost partials (fpHelpers.cuh:299)
     int ee;
+    const int *cost_shift;         // [B] or null: finalCostShift of runiLQR_MPC_GPU (MPCHelpers.cuh:876) -- the pose terms take their final weights from knot N-1-shift on
     int *init_knot;                // [B] EE_COST quirk of the receding-horizon path, see select_kernel mode 1 (0 everywhere else)
     const float *xTarget;          // [B][n] or null: the nominal-state terms measure x from it (receding-horizon path, MPCHelpers.cuh:900)
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;
@@ -595,9 +596,9 @@ __device__ __forceinline__ float ee_add_nominal(const float *x, const float *xt,
     return FMA(0.5f, FMA(MUL(Qq, dq), dq, MUL(MUL(Qqd, dqd), dqd)), cost);
 }
 // joint `ind`'s share of one knot (split costFunc :283-303)
-__device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *xt, const float *u, bool fin, const DevState &S){
+__device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *xt, const float *u, bool fin, bool fin_pose, const DevState &S){
     float cost = 0.f;
-    if (ind == 0){ cost = ADD(cost, ee_pose_cost(ee, goal, fin, S)); }
+    if (ind == 0){ cost = ADD(cost, ee_pose_cost(ee, goal, fin_pose, S)); }
     const float Rk = fin ? 0.f : S.R_EE;
     cost = FMA(MUL(MUL(0.5f, Rk), u[ind]), u[ind], cost);
     return ee_add_nominal(x, xt, ind, fin, cost, S);
@@ -676,7 +677,7 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
         kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
         if (EE){
             // running / final cost of this knot, not on the knots that close a defect (fpHelpers.cuh:259-265)
-            if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, S.xTarget ? S.xTarget + (size_t)b*n : nullptr, s.u, k == N - 1, S)); }
+            if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, S.xTarget ? S.xTarget + (size_t)b*n : nullptr, s.u, k == N - 1, k >= N - 1 - (S.cost_shift ? S.cost_shift[b] : 0), S)); }
         }
         // Euler step (integrators.cuh:31-35)
         if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
@@ -881,13 +882,14 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         // pose (unweighted, as the reference has it) plus the diagonal weights
         const float Rk = fin ? 0.f : S.R_EE;
         const float *xt = S.xTarget ? S.xTarget + (size_t)b*n : nullptr;
+        const bool finp = k >= N - 1 - (S.cost_shift ? S.cost_shift[b] : 0);       // pose terms: final weights (finalCostShift)
         for (int r = l; r < nm; r += LANES){
             float val = 0.f;
             if (r < np){
                 float v2 = 0.f;
                 #pragma unroll
                 for (int i = 0; i < 6; i++){
-                    const float dl = SUB(s.ee[i], xg[i]), Q = fin ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
+                    const float dl = SUB(s.ee[i], xg[i]), Q = finp ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
                     v2 = FMA(MUL(Q, dl), s.dee[r*6+i], v2);
                 }
                 val = ADD(val, v2);
@@ -910,7 +912,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         if (mode == 1 && l == 0){
             float cost = 0.f;
             for (int ind = 0; ind < np; ind++){
-                if (ind == 0){ cost = ADD(cost, ee_pose_cost(s.ee, xg, fin, S)); }
+                if (ind == 0){ cost = ADD(cost, ee_pose_cost(s.ee, xg, finp, S)); }
                 cost = FMA(MUL(MUL(0.5f, Rk), s.u[ind]), s.u[ind], cost);
                 cost = ee_add_nominal(s.x, xt, ind, fin, cost, S);
             }

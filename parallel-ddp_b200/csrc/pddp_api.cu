@@ -42,6 +42,7 @@ struct pddp_solver {
     double last_ms = 0; int last_launches = 0;
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
     float *d_xTarget = nullptr;
+    int *d_cost_shift = nullptr; bool use_cost_shift = false;
     std::map<std::string, std::pair<void*, size_t>> arrays;
 };
 
@@ -384,6 +385,17 @@ extern "C" int pddp_set_x_target(pddp_handle h, const float *xTarget){
     return 0;
 }
 
+// runiLQR_MPC_GPU's use_cost_shift argument (MPCHelpers.cuh:866,876): finalCostShift = shiftAmount of the step.  EE_COST only (the
+// joint-space cost ignores it, as in the reference).
+extern "C" int pddp_mpc_set_cost_shift(pddp_handle h, int use_cost_shift){
+    if (!h){ return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    if (use_cost_shift && !h->d_cost_shift){ void *q = nullptr; CK(cudaMalloc(&q, (size_t)h->S.B*sizeof(int))); CK(cudaMemset(q, 0, (size_t)h->S.B*sizeof(int))); h->d_cost_shift = (int*)q; h->allocs.push_back(q); }
+    h->use_cost_shift = use_cost_shift != 0;
+    h->S.cost_shift = nullptr;                                        // set per step by pddp_mpc_step, cleared after it
+    return 0;
+}
+
 extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_init){
     if (!h){ return PDDP_E_INVALID; }
     if (!x_init || !u_init){ h->err = "null input"; return PDDP_E_INVALID; }
@@ -432,6 +444,7 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
         flags[B + b] = (h->mpc_lss[b] > 10 /* SOLVES_TO_RESET, MPCHelpers.cuh:34-36 */ || clear_vars) ? 1 : 0;
     }
     CK(cudaMemcpyAsync(h->d_mpc_flags, flags.data(), 2*(size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (h->use_cost_shift && S.ee){ CK(cudaMemcpyAsync(h->d_cost_shift, flags.data(), (size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream)); S.cost_shift = h->d_cost_shift; }
     CK(cudaMemcpyAsync(h->d_xActual, xActual, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.xGoal, xGoal, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
     // loadVarsGPU_MPC + hand-over; the cost-to-go buffers keep their roles: the first backward pass must seed its blocks from the
@@ -445,7 +458,7 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     if ((rc = launch_init(h, 0))){ return rc; }
     S.iter_cap = max_iter;
     rc = run_iterations(h, nullptr, 1);
-    S.iter_cap = S.max_iter;
+    S.iter_cap = S.max_iter; S.cost_shift = nullptr;
     if (rc){ return rc; }
     // success bookkeeping (MPCHelpers.cuh:987-991, 757-758) needs the step-size trace on the host
     std::vector<int> aout((size_t)B*L), its(B); std::vector<float> jout((size_t)B*L);

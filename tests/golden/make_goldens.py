@@ -28,6 +28,8 @@ def run(N, *args):
     exe = os.path.join(REF, f"ref_mpc_N{N}" if args and args[0] == "mpc" else f"ref_driver_N{N}")
     if args and args[0] == "mpc_ee":                    # receding horizon built with EE_COST 1 (ref_mpc.cu -DEE_COST=1)
         exe, args = os.path.join(REF, f"ref_mpc_ee_N{N}"), ("mpc",) + tuple(args[1:])
+        if "CS" in args:                                # use_cost_shift = 1: the flag follows the output file on ref_mpc's command line
+            args = tuple(a for a in args if a != "CS") + (1,)
     if args and str(args[0]).startswith("ee_"):          # end-effector cost build (EE_COST 1): oracle/ref_harness/ref_ee.cu
         exe, args = os.path.join(REF, f"ref_ee_N{N}"), (args[0][3:],) + tuple(args[1:])
     print("+", exe, *args, flush=True)
@@ -64,7 +66,8 @@ def jobs(hw):
                 (32, ("ee_solve", "G", 0, 4, 0.0), "ee_solve_G_N32_s0-3_tol0"),
                 (128, ("ee_solve", "G", 0, 2, 0.0), "ee_solve_G_N128_s0-1_tol0"),
                 (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1"),
-                (32, ("mpc_ee", 5, 8, 2, 4), "mpc_ee_G_N32_s5")]
+                (32, ("mpc_ee", 5, 8, 2, 4), "mpc_ee_G_N32_s5"),
+                (32, ("mpc_ee", 7, 6, 3, 5, "CS"), "mpc_ee_cs_G_N32_s7")]      # use_cost_shift = 1
     return out
 
 
