@@ -859,11 +859,12 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     const float *xg = S.xGoal + b*n;
     float *gg = S.g + ((size_t)b*N + k)*G_STRIDE;
     const bool fin = (k == N - 1);
+    // joint-space cost; the end-effector cost needs the tool pose and follows the gradient below
     if (!S.ee){
-    for (int e = l; e < nm; e += LANES){
-        if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
-        else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
-    }
+        for (int e = l; e < nm; e += LANES){
+            if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
+            else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
+        }
     }
     if (write_H && !S.ee){
         float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
