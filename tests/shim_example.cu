@@ -1,6 +1,8 @@
 // Compile check of include/pddp_shim.cuh: the call sequence of examples/WAFR_iLQR_examples.cu::testGPU (lines 301-361)
 // with the reference's argument lists, against libpddp.so.  Run on a GPU box: prints one summary line per solve.
-#define EE_COST 0
+#ifndef EE_COST
+#define EE_COST 0        // -DEE_COST=1: the end-effector cost build of the example (WAFR_iLQR_examples.cu:37-43,101-104)
+#endif
 #define TOL_COST 0.0
 #define NUM_TIME_STEPS 32
 #define MAX_ITER 5
@@ -16,6 +18,9 @@ int main(){
     std::vector<T> x0(ld_x*NUM_TIME_STEPS), u0(ld_u*NUM_TIME_STEPS); T Jout[MAX_ITER+1]; int alphaOut[MAX_ITER+1];
     double tTime, initTime, fsim[MAX_ITER], fsw[MAX_ITER], bp[MAX_ITER], nis[MAX_ITER];
     pddp_make_inputs_kuka(NUM_TIME_STEPS, 1, 0, x0.data(), u0.data(), xGoal);
+#if EE_COST
+    { const T pose[6] = {(T)0.3638, (T)0.0, (T)1.0628, (T)(0.5*PI), (T)0.0, (T)(0.5*PI)}; for (int i = 0; i < STATE_SIZE; i++){ xGoal[i] = i < 6 ? pose[i] : (T)0; } }
+#endif
     runiLQR_GPU<T>(x0.data(), u0.data(), nullptr, nullptr, nullptr, nullptr, xGoal, Jout, alphaOut, 0, 1, 1, &tTime, fsim, fsw, bp, nis, &initTime, streams,
                    d_x, h_d_x, d_xp, d_xp2, d_u, h_d_u, d_up, d_P, d_p, d_Pp, d_pp, d_AB, d_H, d_g, d_KT, d_du, d_d, h_d_d, d_dp, d_dT, d, d_ApBK, d_Bdu, d_dM,
                    alpha, d_alpha, alphaIndex, d_JT, J, dJexp, d_dJexp, d_xGoal, err, d_err, ld_x, ld_u, ld_P, ld_p, ld_AB, ld_H, ld_g, ld_KT, ld_du, ld_d, ld_A, d_I, d_Tbody);
