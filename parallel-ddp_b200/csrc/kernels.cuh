@@ -604,10 +604,13 @@ __device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const f
     return ee_add_nominal(x, xt, ind, fin, cost, S);
 }
 
-template <bool EE>
+// LANES = 16: two candidates per warp, the throughput shape (27 % faster than 32 lanes once every scheduler has several warps).
+// LANES = 32: one candidate per warp, the latency shape for small batches (fewer passes per phase: 13 % faster per knot when the
+// whole launch fits the machine with one warp per scheduler).  Same arithmetic either way; the host picks (launch_sim_any).
+template <bool EE, int LANES>
 __global__ void sim_kernel(DevState S, int b0, int n_cand){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, m = kuka::NU, LANES = SIM_LANES, GPW = 32 / SIM_LANES;
+    constexpr int n = kuka::NX, m = kuka::NU, GPW = 32 / LANES;
     float *sI = reinterpret_cast<float*>(smem_raw);            // 252
     float *sTb = sI + 36*kuka::NB;                             // 252
     float *sxg = sTb + 36*kuka::NB;                            // 16

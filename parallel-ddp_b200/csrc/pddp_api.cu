@@ -43,6 +43,7 @@ struct pddp_solver {
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
     float *d_xTarget = nullptr;
     int *d_cost_shift = nullptr; bool use_cost_shift = false;
+    int sim_lanes = 16;                                                        // lanes per simulated trajectory (16: throughput shape, 32: latency shape)
     std::map<std::string, std::pair<void*, size_t>> arrays;
 };
 
@@ -146,8 +147,13 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
     CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
     CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
-    CKC(cudaFuncSetAttribute(sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
-    CKC(cudaFuncSetAttribute(sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    CKC(cudaFuncSetAttribute(sim_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+    // latency shape of the simulation when one warp per (interval, candidate) of the WHOLE batch still leaves a scheduler per warp
+    { const char *env = std::getenv("PDDP_SIM_LANES"); const int v = env ? std::atoi(env) : 0;
+      h->sim_lanes = (v == 16 || v == 32) ? v : (((long long)B*A*M <= 4LL*h->num_sms) ? 32 : 16); }
     CKC(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sel));
     CKC(cudaFuncSetAttribute(nis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nis));
     CKC(cudaFuncSetAttribute(unit_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_udyn));
@@ -206,6 +212,15 @@ static int launch_reset(pddp_handle h, int ignore_first, int clear){
     CK(cudaGetLastError());
     return 0;
 }
+// forward simulation of n_cand candidates of problems [b0, b0+nb): cost variant and lane shape picked here
+static void launch_sim_any(pddp_handle h, cudaStream_t st, int b0, int nb, int n_cand){
+    DevState &S = h->S; const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw), cta = 32*S.M;
+    if (h->sim_lanes == 32){
+        if (S.ee){ sim_kernel<true, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); } else { sim_kernel<false, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); }
+    } else {
+        if (S.ee){ sim_kernel<true, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); } else { sim_kernel<false, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); }
+    }
+}
 static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
     DevState &S = h->S; const int B = S.B, N = S.N, A = S.A, n = S.n;
     S.rolled_out = rollout ? 1 : 0;
@@ -213,8 +228,7 @@ static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInit
         // loadVarsGPU's forward rollout (nisInitHelpers.cuh:646-651): candidate 0 starts as the given trajectory and is simulated
         // with alpha[0], du = 0 and the feedback gains KT around it; the result (x, u, defects) becomes the start trajectory
         CK(cudaMemcpy2DAsync(S.x, (size_t)A*N*n*4, S.xp, (size_t)N*n*4, (size_t)N*n*4, B, cudaMemcpyDeviceToDevice, h->stream));
-        if (S.ee){ sim_kernel<true><<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1); }
-        else { sim_kernel<false><<<B*((1 + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, h->stream>>>(S, 0, 1); }
+        launch_sim_any(h, h->stream, 0, B, 1);
         h->launches += 1;
     }
     nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, rollout ? 2 : 1, 1, 0, S.B);
@@ -240,8 +254,7 @@ static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
 }
 static int launch_sim(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    if (S.ee){ sim_kernel<true><<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A); }
-    else { sim_kernel<false><<<nb*((S.A + 32/SIM_LANES - 1)/(32/SIM_LANES)), 32*S.M, h->smem_sim, st>>>(S, b0, S.A); }
+    launch_sim_any(h, st, b0, nb, S.A);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
