@@ -13,6 +13,9 @@
  * fused-multiply-add pattern nvcc emits for the reference's device code) against the
  * reference's GPU run (`trace G`, `unit G`) -- see tests/test_oracle_golden.py.
  *
+ * The end-effector cost path (EE_COST 1: orc_ee_*, orc_cfg.ee_cost / xTarget / final_cost_shift) is pinned the same way against
+ * oracle/_ref/ref_ee_N* (`unit H`, `unit G`, `solve G`, `warm G`) and ref_mpc_ee_N32 (receding horizon).
+ *
  * All matrices are column-major with leading dimension = row count, per-knot arrays are
  * contiguous [k][col][row] exactly as the reference allocates them (nisInitHelpers.cuh:776,797-798).
  */
