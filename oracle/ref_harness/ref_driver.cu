@@ -19,13 +19,22 @@
  *   unit   <G|H>   <nsamples> <seed> <out.bin>                       (dynamics / gradient / cost on random x,u)
  *   time   <G|C|P> <seed0> <nseeds> <tol_cost>                       (prints one summary line)
  */
+#ifndef PLANT
+#define PLANT 4
+#endif
 #define EE_COST 0
+#if PLANT == 4
 #define USE_WAFR_URDF 1
 #define _Q1 0.1
 #define _Q2 0.001
 #define _R  0.0001
 #define _QF1 1000.0
 #define _QF2 1000.0
+#endif
+// PLANT 1-3 (pendulum, cart-pole, quadrotor): the plant files of the reference still have their v0.1 signatures and do not compile
+// inside config.cuh at HEAD.  oracle/Makefile builds those configurations against a config.cuh whose three plant
+// #include lines are redirected (sed, into oracle/_ref/gen/) to ref_harness/adapt_plant.cuh, which includes the SAME reference
+// plant files inside a namespace and forwards the v0.2 call signatures to them.  Every other reference file is compiled as is.
 // run-time cost tolerance: the macro is only used in host code (nisInitHelpers.cuh:393,395,456,512)
 double g_tol_cost = 0.0;
 #define TOL_COST g_tol_cost
@@ -65,6 +74,7 @@ static std::string nm(const char *base, int iter, const char *phase){
 static void loadXU_seeded(T *x, T *u, T *xGoal, int ld_x, int ld_u, unsigned seed){
 	std::default_random_engine eng(seed);
 	std::normal_distribution<double> dist(0.0, 0.001);
+#if PLANT == 4
 	for (int k = 0; k < NT; k++){
 		T *xk = x + k*ld_x;
 		xk[0] = -0.5*PI;	xk[1] = 0.25*PI;	xk[2] = 0.167*PI;
@@ -77,6 +87,34 @@ static void loadXU_seeded(T *x, T *u, T *xGoal, int ld_x, int ld_u, unsigned see
 		uk[3] = 47.0724;	uk[4] = 2.5993;		uk[5] = -7.0290;	uk[6] = -0.0907;
 	}
 	const T temp[] = {0,0,0,-0.25*PI,0,0.25*PI,0.5*PI,0,0,0,0,0,0,0};
+#else
+	// the other plants of the example (WAFR_iLQR_examples.cu:19-33,72-78,87-90,110-115): draws in knot order, state order
+	for (int k = 0; k < NT; k++){
+		T *xk = x + k*ld_x;
+	#if PLANT == 1
+		xk[0] = 0.0;	xk[1] = static_cast<T>(dist(eng));
+	#elif PLANT == 2
+		xk[0] = 0.0;	xk[1] = 0.0;	xk[2] = static_cast<T>(dist(eng));	xk[3] = static_cast<T>(dist(eng));
+	#elif PLANT == 3
+		for (int k2 = 0; k2 < STATE_SIZE; k2++){if (k2 == 2){xk[k2] = 0.5;} else if (k2 >= NUM_POS){xk[k2] = static_cast<T>(dist(eng));} else{xk[k2] = 0.0;}}
+	#endif
+	}
+	for (int k = 0; k < NT; k++){
+		T *uk = u + k*ld_u;
+	#if PLANT == 3
+		for (int k2 = 0; k2 < CONTROL_SIZE; k2++){uk[k2] = 1.22625;}
+	#else
+		uk[0] = 0.01;
+	#endif
+	}
+	#if PLANT == 1
+	const T temp[] = {3.1416, 0.0};
+	#elif PLANT == 2
+	const T temp[] = {0.0, 3.1416, 0.0, 0.0};
+	#elif PLANT == 3
+	const T temp[] = {7.0, 10.0, 0.5, 0,0,0,0,0,0,0,0,0};
+	#endif
+#endif
 	for (int i = 0; i < STATE_SIZE; i++){xGoal[i] = temp[i];}
 }
 
@@ -342,10 +380,21 @@ static int run_trace_host(unsigned seed, int maxdump){
 	while (1){
 		bool dmp = iter <= maxdump;
 		// backward pass: M_BLOCKS_B independent blocks (bpHelpers.cuh:422-481, FORCE_PARALLEL reads Pp/pp)
-		for (int b = 0; b < M_BLOCKS_B; b++){
-			threadDesc_t desc; desc.tid = b; desc.dim = M_BLOCKS_B; desc.reps = 1;
-			backPassThreaded<T>(desc, AB, P, p, Pp, pp, H, g, KT, du, ds[alphaIndex], ApBK, Bdu, xs[alphaIndex], xp2, dJexp, err, ld_AB, ld_P, ld_p, ld_H, ld_g, ld_KT, ld_du, ld_A, ld_d, ld_x, rho);
+		// a block whose Huu is not positive definite reports err (only the 1-D and 4-D inverses can): rho up, P,p <- Pp,pp, again
+		// (backwardPassGPU bpHelpers.cuh:497-511)
+		int n_retry = 0;
+		while (1){
+			int fail = 0;
+			for (int b = 0; b < M_BLOCKS_B; b++){
+				threadDesc_t desc; desc.tid = b; desc.dim = M_BLOCKS_B; desc.reps = 1;
+				backPassThreaded<T>(desc, AB, P, p, Pp, pp, H, g, KT, du, ds[alphaIndex], ApBK, Bdu, xs[alphaIndex], xp2, dJexp, err, ld_AB, ld_P, ld_p, ld_H, ld_g, ld_KT, ld_du, ld_A, ld_d, ld_x, rho);
+			}
+			for (int b = 0; b < M_BLOCKS_B; b++){fail |= err[b];}
+			if (!fail){break;}
+			drho = max(drho*static_cast<T>(RHO_FACTOR),static_cast<T>(RHO_FACTOR)); rho = min(rho*drho, static_cast<T>(RHO_MAX));
+			memcpy(P, Pp, ld_P*DIM_P_c*NT*sizeof(T)); memcpy(p, pp, ld_p*NT*sizeof(T)); n_retry++;
 		}
+		if (dmp){int si[1] = {n_retry}; dumpi(nm("retries",iter,"bp").c_str(), si, 1);}
 		if (dmp){
 			dumpf(nm("P",iter,"bp").c_str(), P, ld_P*DIM_P_c*NT); dumpf(nm("p",iter,"bp").c_str(), p, ld_p*NT);
 			dumpf(nm("KT",iter,"bp").c_str(), KT, ld_KT*DIM_KT_c*NT); dumpf(nm("du",iter,"bp").c_str(), du, ld_du*NT);
