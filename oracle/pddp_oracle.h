@@ -73,6 +73,7 @@ typedef struct {
 } orc_ws;
 
 void  orc_default_cfg_kuka(orc_cfg *c, int N);                 /* headline constants, SURVEY A.1 (I/Tbody must be filled by caller) */
+void  orc_default_cfg_plant(orc_cfg *c, int plant, int N, int n_alpha, int integrator);   /* PLANT 1-3: config.cuh:21-61 + the plants' cost weights */
 orc_ws *orc_ws_alloc(const orc_cfg *c);
 void  orc_ws_free(orc_ws *w);
 
@@ -86,6 +87,7 @@ void  orc_integrator(const orc_cfg *c, const float *x, const float *u, float *xn
 void  orc_integrator_gradient(const orc_cfg *c, const float *x, const float *u, float *AB, float *qdd_out);
 float orc_cost(const orc_cfg *c, const float *x, const float *u, const float *xg, int k);               /* cost_*.cuh costFunc */
 void  orc_cost_grad(const orc_cfg *c, float *H, float *g, const float *x, const float *u, const float *xg, int k);
+void  orc_dynamics_gradient_any(const orc_cfg *c, const float *x, const float *u, float *qdd, float *dqdd /*[npos*(n+m)]*/);   /* dynamicsGradient of any plant */
 
 /* end-effector cost plug-ins (EE_COST 1) */
 void  orc_ee_pos(const orc_cfg *c, const float *x, float *ee /*[6]*/, float *dee /*[7][6] or NULL*/);           /* compute_eePos dynamics_arm.cuh:1877-1923 */

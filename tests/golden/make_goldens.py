@@ -26,6 +26,8 @@ _DROP = re.compile(r"it\d+\.(nis|init)\.[xud]([1-9]|1\d)$")
 
 def run(N, *args):
     exe = os.path.join(REF, f"ref_mpc_N{N}" if args and args[0] == "mpc" else f"ref_driver_N{N}")
+    if isinstance(N, str):                              # pendulum / cart-pole / quadrotor builds: ref_p<plant>_i<integrator>_N<knots>_a<alphas>
+        exe = os.path.join(REF, "ref_" + N)
     if args and args[0] == "mpc_ee":                    # receding horizon built with EE_COST 1 (ref_mpc.cu -DEE_COST=1)
         exe, args = os.path.join(REF, f"ref_mpc_ee_N{N}"), ("mpc",) + tuple(args[1:])
         if "CS" in args:                                # use_cost_shift = 1: the flag follows the output file on ref_mpc's command line
@@ -52,6 +54,15 @@ def jobs(hw):
            (128, ("trace", t, 0, 0.0, 1), f"trace_{t}_N128_s0_tol0"),
            # end-effector cost: cost / gradient / Hessian of costGradientHessianKern (G) / ...Threaded (H) on random states
            (32, ("ee_unit", t, 64, 7), f"ee_unit_{t}")]
+    # PLANT 1-3 (oracle/ref_harness/adapt_plant.cuh): plant functions + integrator gradient on random states, traces of whole solves
+    for cfg, seeds in (("p1_i3_N32_a1", (0,)), ("p1_i2_N32_a4", (1,)), ("p2_i3_N64_a8", (0, 2)), ("p2_i1_N32_a8", (1,)),
+                       ("p3_i3_N64_a16", (0,)), ("p3_i2_N32_a16", (1,))):
+        out.append((cfg, ("unit", t, 96, 7), f"{cfg}_unit_{t}"))
+        for sd in seeds:
+            out.append((cfg, ("trace", t, sd, 0.0 if sd < 2 else 0.0001, 2 if "N64" not in cfg else 1), f"{cfg}_trace_{t}_s{sd}"))
+    if hw == "G":
+        out += [(cfg, ("solve", "G", 0, 4, 0.0), f"{cfg}_solve_G_s0-3") for cfg in
+                ("p1_i3_N32_a1", "p1_i2_N32_a4", "p2_i3_N64_a8", "p2_i1_N32_a8", "p3_i3_N64_a16", "p3_i2_N32_a16", "p3_i3_N256_a32")]
     if hw == "G":
         out += [(128, ("solve", "G", 0, 64, 0.0), "solve_G_N128_s0-63_tol0"),
                 (128, ("solve", "G", 0, 64, 0.0001), "solve_G_N128_s0-63_tol1e-4"),

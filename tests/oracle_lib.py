@@ -65,6 +65,9 @@ def lib(fma=False):
     cp = C.POINTER(Cfg)
     wp = C.POINTER(Ws)
     L.orc_default_cfg_kuka.argtypes = [cp, C.c_int]
+    L.orc_default_cfg_plant.argtypes = [cp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_dynamics.argtypes = [cp, FP, FP, FP]
+    L.orc_dynamics_gradient_any.argtypes = [cp, FP, FP, FP, FP]
     L.orc_ws_alloc.argtypes = [cp]; L.orc_ws_alloc.restype = wp
     L.orc_ws_free.argtypes = [wp]
     L.orc_kuka_dynamics.argtypes = [cp, FP, FP, FP]
@@ -121,6 +124,22 @@ def kuka_cfg(N, fma=False, tol_cost=0.0, host_expred=False, ee_weights=None, x_t
         c.use_xtarget = 1
         c.xTarget[:14] = [float(v) for v in x_target]
     return c
+
+
+def plant_cfg(plant, N, n_alpha, integrator, fma=False, tol_cost=0.0, host_expred=False):
+    """PLANT 1-3 (pendulum, cart-pole, quadrotor) with the reference's defaults (config.cuh:21-61 and the plants' cost weights)."""
+    L = lib(fma)
+    c = Cfg()
+    L.orc_default_cfg_plant(C.byref(c), plant, N, n_alpha, integrator)
+    c.tol_cost = tol_cost
+    c.expred_host_order = 1 if host_expred else 0
+    return c
+
+
+def parse_plant_tag(tag):
+    """'p2_i3_N64_a8' -> (plant, integrator, N, n_alpha): the naming of oracle/Makefile's PLANT 1-3 reference builds"""
+    p, i, n, a = tag.split("_")[:4]
+    return int(p[1:]), int(i[1:]), int(n[1:]), int(a[1:])
 
 
 class WsView:
