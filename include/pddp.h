@@ -31,7 +31,7 @@ extern "C" {
 
 /* Run-time form of the reference's compile-time flag system (config.cuh:21-136). */
 typedef struct pddp_config {
-    int   plant;          /* PLANT (config.cuh:21-61); 4 = Kuka iiwa14 */
+    int   plant;          /* PLANT (config.cuh:21-61): 1 pendulum, 2 cart-pole, 3 quadrotor, 4 Kuka iiwa14, or a registered plug-in */
     int   N;              /* NUM_TIME_STEPS: power of two in [32,1024] (cudaUtils.h:187-207 reduction trees) */
     int   n_alpha;        /* NUM_ALPHA <= PDDP_MAX_ALPHA */
     int   M;              /* M_BLOCKS = M_BLOCKS_B = M_BLOCKS_F (config.cuh:90-92), must divide N */
@@ -59,6 +59,24 @@ typedef struct pddp_solver *pddp_handle;
 
 /* Fill *cfg with the reference's Kuka defaults for the WAFR iLQR example (config.cuh:43-58, WAFR_iLQR_examples.cu:4-11). */
 void pddp_default_config_kuka(pddp_config *cfg, int N, int batch);
+
+/* The same for any built-in plant: PLANT 1 pendulum, 2 cart-pole, 3 quadrotor take config.cuh:21-136's defaults (RK3, M_BLOCKS 4,
+ * NUM_ALPHA 32 / ALPHA_BASE 0.75 -- quadrotor 16 / 0.5 --, TOTAL_TIME 4, RHO_INIT 10 / 10 / 1, MAX_DEFECT_SIZE 1 / 0.75 / 1) and the
+ * weights of plants/cost_{pend,cart,quad}.cuh mapped onto Q1 (positions; quadrotor: x y z), Q2 (rates; quadrotor: roll pitch yaw,
+ * its rates are weighted 2.0 by the plant), R, QF1, QF2; PLANT 4 = pddp_default_config_kuka. */
+int pddp_default_config(pddp_config *cfg, int plant, int N, int batch);
+/* NUM_POS, STATE_SIZE, CONTROL_SIZE of a plant (config.cuh:21-61); any pointer may be NULL */
+int pddp_plant_dims(int plant, int *num_pos, int *state_size, int *control_size);
+
+/* ---- plant plug-ins (include/pddp_plant.h, parallel-ddp_b200/csrc/plugin/pddp_plugin.cuh): a plant written as a
+ * reference-style header (dynamics, dynamicsGradient, costFunc, costGrad, initI, initT with the signatures of plants/dynamics_arm.cuh:
+ * 2095-2097,2165-2167 and plants/cost_arm.cuh:128-130,156-158) and compiled around csrc/plant_tu.cu becomes available to pddp_create
+ * under its own pddp_config.plant number.  pddp_load_plant_library dlopens such a library and returns the plant number (>= 1) or a
+ * negative code; pddp_plant_error() has the reason. */
+struct pddp_plant_ops;
+int pddp_register_plant(const struct pddp_plant_ops *ops);
+int pddp_load_plant_library(const char *path);
+const char *pddp_plant_error(void);
 
 /* replaces allocateMemory_GPU (nisInitHelpers.cuh:766-861): owns every device array, stream and the model constants */
 int pddp_create(const pddp_config *cfg, pddp_handle *out);
@@ -101,6 +119,9 @@ int pddp_mpc_set_cost_shift(pddp_handle h, int use_cost_shift);
  * gv->d_xTarget (MPCHelpers.cuh:900), so a receding-horizon caller sets it.  HOST [batch][n]; NULL removes it. */
 int pddp_set_x_target(pddp_handle h, const float *xTarget);
 
+/* Inputs of the example for any built-in plant (WAFR_iLQR_examples.cu:19-33,72-78,87-90,110-115), seeded like pddp_make_inputs_kuka */
+int pddp_make_inputs(int plant, int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal);
+
 /* Consumer side of the hand-off: replaces getHardwareControls (DDPHelpers/MPCHelpers.cuh:817-858), the host function that turns
  * the published plan and a measured state into the joint command.  Zero-order hold on u and KT, first-order hold on x:
  *   steps = (tActual - t0) / (time_step * 1e6)   [times in microseconds, time_step = TOTAL_TIME/(N-1) in seconds]
@@ -118,6 +139,10 @@ int pddp_hardware_controls(int N, double time_step, const float *x, const float 
  * dynamics (plants/dynamics_arm.cuh:2095), _integratorGradient (utils/integrators.cuh:38-53) */
 int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int n, float *qdd);
 int pddp_unit_integrator_gradient(pddp_handle h, const float *x, const float *u, int n, float *AB, float *qdd);
+/* plug-in plants: x_{k+1} of _integrator (utils/integrators.cuh:24-36,56-83,123-160) and costFunc / costGrad (plants/cost_*.cuh) for n
+ * samples; knot[i] is the k argument (N-1 selects the final cost), xGoal one goal for all samples, H [n][(n+m)^2], g [n][n+m] */
+int pddp_unit_integrator(pddp_handle h, const float *x, const float *u, int n, float *xnext);
+int pddp_unit_cost(pddp_handle h, const float *x, const float *u, const float *xGoal, const int *knot, int n, float *J, float *H, float *g);
 
 /* ---- phase-level entry points on the solver's device state (for knot-level parity tests and ncu captures) ----------
  * The state is addressed by array name: "x","u","d" ([batch][n_alpha][N][.]), "xp","xp2","up","dp","AB","H","g","P","p",

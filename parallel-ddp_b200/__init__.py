@@ -45,6 +45,8 @@ EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
            "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
+           "pddp_default_config", "pddp_plant_dims", "pddp_register_plant", "pddp_load_plant_library", "pddp_plant_error", "pddp_make_inputs",
+           "pddp_unit_integrator", "pddp_unit_cost",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -92,6 +94,14 @@ def load_library():
     L.pddp_traj_f_decode.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_longlong), IP, IP, IP, FP, FP, FP, C.c_long, C.c_long, C.c_long]; L.pddp_traj_f_decode.restype = C.c_long
     L.pddp_traj_f_pack_reference.argtypes = [C.c_longlong, FP, FP, FP, C.c_int, C.c_int, C.c_void_p, C.c_long]; L.pddp_traj_f_pack_reference.restype = C.c_long
     L.pddp_mpc_step.argtypes = [H, FP, FP, IP, C.c_int, C.c_int, C.c_int, FP, FP, FP, FP, IP, IP, IP]
+    L.pddp_default_config.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int]
+    L.pddp_plant_dims.argtypes = [C.c_int, IP, IP, IP]
+    L.pddp_register_plant.argtypes = [C.c_void_p]
+    L.pddp_load_plant_library.argtypes = [C.c_char_p]
+    L.pddp_plant_error.argtypes = []; L.pddp_plant_error.restype = C.c_char_p
+    L.pddp_make_inputs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, FP, FP, FP]
+    L.pddp_unit_integrator.argtypes = [H, FP, FP, C.c_int, FP]
+    L.pddp_unit_cost.argtypes = [H, FP, FP, FP, IP, C.c_int, FP, FP, FP]
     _lib = L
     return L
 
@@ -103,6 +113,43 @@ def default_config_kuka(N=128, batch=1, **over):
     for k, v in over.items():
         setattr(c, k, v)
     return c
+
+
+def default_config(plant, N, batch=1, **over):
+    """pddp_default_config: the reference's compile-time defaults of a plant (config.cuh:21-136) as a run-time Config."""
+    L = load_library()
+    c = Config()
+    if L.pddp_default_config(C.byref(c), plant, N, batch) != 0:
+        raise PddpError(f"no defaults for PLANT {plant}")
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def plant_dims(plant):
+    """(NUM_POS, STATE_SIZE, CONTROL_SIZE) of a built-in or registered plant."""
+    L = load_library(); a, b, c = C.c_int(), C.c_int(), C.c_int()
+    if L.pddp_plant_dims(plant, C.byref(a), C.byref(b), C.byref(c)) != 0:
+        raise PddpError(f"unknown PLANT {plant}")
+    return a.value, b.value, c.value
+
+
+def load_plant_library(path):
+    """Register a plant plug-in library (include/pddp_plant.h); returns its PLANT number."""
+    L = load_library()
+    rc = L.pddp_load_plant_library(os.fsencode(path))
+    if rc < 1:
+        raise PddpError(f"pddp_load_plant_library({path}): {L.pddp_plant_error().decode()}")
+    return rc
+
+
+def make_inputs(plant, N, batch, seed0=0):
+    """Initial guess and goal of the reference's example for any built-in plant (WAFR_iLQR_examples.cu:19-33,67-121)."""
+    L = load_library(); _, n, m = plant_dims(plant)
+    x0 = np.zeros((batch, N, n), np.float32); u0 = np.zeros((batch, N, m), np.float32); xg = np.zeros((batch, n), np.float32)
+    if L.pddp_make_inputs(plant, N, batch, seed0, x0.ctypes.data_as(FP), u0.ctypes.data_as(FP), xg.ctypes.data_as(FP)) != 0:
+        raise PddpError(f"no example inputs for PLANT {plant}")
+    return x0, u0, xg
 
 
 def _f(a):
@@ -162,9 +209,9 @@ class Solver:
         if rc != 0:
             raise PddpError(f"pddp_create failed ({rc}): {self.L.pddp_last_error(None).decode()}")
         B, N, A, M = cfg.batch, cfg.N, cfg.n_alpha, cfg.M
-        n, m = 14, 7
+        npos, n, m = plant_dims(cfg.plant)
         nm = n + m
-        self.n, self.m = n, m
+        self.n, self.m, self.npos = n, m, npos
         f, i = np.float32, np.int32
         self.shapes = dict(x=((B, A, N, n), f), u=((B, A, N, m), f), d=((B, A, N, n), f), xp=((B, N, n), f), xp2=((B, N, n), f),
                            up=((B, N, m), f), dp=((B, N, n), f), AB=((B, N, nm, n), f), H=((B, N, nm, nm), f), g=((B, N, nm), f),
@@ -183,15 +230,15 @@ class Solver:
     def mpc_init(self, x_init, u_init):
         """Start plan of the receding-horizon loop: x_init [B,N,14], u_init [B,N,7]; they also become the published plan."""
         B, N = self.cfg.batch, self.cfg.N
-        self.mpc_x, px = _f(np.broadcast_to(x_init, (B, N, 14)).copy()); self.mpc_u, pu = _f(np.broadcast_to(u_init, (B, N, 7)).copy())
-        self.mpc_KT = np.zeros((B, N, 98), np.float32)
+        self.mpc_x, px = _f(np.broadcast_to(x_init, (B, N, self.n)).copy()); self.mpc_u, pu = _f(np.broadcast_to(u_init, (B, N, self.m)).copy())
+        self.mpc_KT = np.zeros((B, N, self.n*self.m), np.float32)
         self._ck(self.L.pddp_mpc_init(self.h, px, pu), "pddp_mpc_init")
 
     def mpc_step(self, xActual, xGoal, shiftAmount, max_iter, clear_vars=0, ignoreFirstDefectFlag=0):
         """One runiLQR_MPC_GPU call per problem.  Returns dict(x, u, KT (the published plan, updated in place), Jout, alphaOut, iters,
         last_successful_solve)."""
         B = self.cfg.batch; L1 = self.cfg.max_iter + 1
-        xa, pxa = _f(np.broadcast_to(xActual, (B, 14))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        xa, pxa = _f(np.broadcast_to(xActual, (B, self.n))); xg, pg = _f(np.broadcast_to(xGoal, (B, self.n)))
         sh = np.ascontiguousarray(np.broadcast_to(shiftAmount, (B,)), dtype=np.int32)
         Jout = np.empty((B, L1), np.float32); aOut = np.empty((B, L1), np.int32); iters = np.empty(B, np.int32); lss = np.empty(B, np.int32)
         rc = self.L.pddp_mpc_step(self.h, pxa, pg, sh.ctypes.data_as(IP), max_iter, clear_vars, ignoreFirstDefectFlag,
@@ -203,8 +250,8 @@ class Solver:
     def set_warm_start(self, KT0, P0, p0, d0):
         """runiLQR_GPU's KT0, P0, p0, d0: [B,N,98], [B,N,196], [B,N,14], [B,N,14] in the reference layouts."""
         B, N = self.cfg.batch, self.cfg.N
-        a, pa = _f(np.broadcast_to(KT0, (B, N, 98))); b, pb = _f(np.broadcast_to(P0, (B, N, 196)))
-        c, pc = _f(np.broadcast_to(p0, (B, N, 14))); d, pd = _f(np.broadcast_to(d0, (B, N, 14)))
+        a, pa = _f(np.broadcast_to(KT0, (B, N, self.n*self.m))); b, pb = _f(np.broadcast_to(P0, (B, N, self.n*self.n)))
+        c, pc = _f(np.broadcast_to(p0, (B, N, self.n))); d, pd = _f(np.broadcast_to(d0, (B, N, self.n)))
         self._ck(self.L.pddp_set_warm_start(self.h, pa, pb, pc, pd), "pddp_set_warm_start")
 
     def runiLQR_GPU(self, x0, u0, xGoal, forwardRolloutFlag=0, clearVarsFlag=1, ignoreFirstDefectFlag=1, want_times=False,
@@ -214,9 +261,9 @@ class Solver:
         B, N = self.cfg.batch, self.cfg.N
         if KT0 is not None:
             self.set_warm_start(KT0, P0, p0, d0)
-        x0, px = _f(np.broadcast_to(x0, (B, N, 14))); u0, pu = _f(np.broadcast_to(u0, (B, N, 7))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        x0, px = _f(np.broadcast_to(x0, (B, N, self.n))); u0, pu = _f(np.broadcast_to(u0, (B, N, self.m))); xg, pg = _f(np.broadcast_to(xGoal, (B, self.n)))
         L1 = self.cfg.max_iter + 1
-        x = np.empty((B, N, 14), np.float32); u = np.empty((B, N, 7), np.float32)
+        x = np.empty((B, N, self.n), np.float32); u = np.empty((B, N, self.m), np.float32)
         Jout = np.empty((B, L1), np.float32); aOut = np.empty((B, L1), np.int32); iters = np.empty(B, np.int32)
         times = np.zeros(6, np.float64)
         rc = self.L.pddp_solve(self.h, px, pu, pg, forwardRolloutFlag, clearVarsFlag, ignoreFirstDefectFlag,
@@ -238,7 +285,7 @@ class Solver:
         """EE_COST: xTarget [B,14] of the nominal-state cost terms (runiLQR_MPC_GPU's gv->xTarget), or None."""
         if xTarget is None:
             self._ck(self.L.pddp_set_x_target(self.h, None), "pddp_set_x_target"); return
-        a, pa = _f(np.broadcast_to(np.asarray(xTarget, np.float32).reshape(-1, 14), (self.cfg.batch, 14)))
+        a, pa = _f(np.broadcast_to(np.asarray(xTarget, np.float32).reshape(-1, self.n), (self.cfg.batch, self.n)))
         self._ck(self.L.pddp_set_x_target(self.h, pa), "pddp_set_x_target")
 
     def mpc_set_cost_shift(self, on):
@@ -259,15 +306,30 @@ class Solver:
     # ---- plant plug-ins -----------------------------------------------------------------------------------------
     def dynamics(self, x, u):
         x, px = _f(x); u, pu = _f(u); n = x.shape[0]
-        qdd = np.empty((n, 7), np.float32)
+        qdd = np.empty((n, self.npos), np.float32)
         self._ck(self.L.pddp_unit_dynamics(self.h, px, pu, n, qdd.ctypes.data_as(FP)), "pddp_unit_dynamics")
         return qdd
 
     def integratorGradient(self, x, u):
         x, px = _f(x); u, pu = _f(u); n = x.shape[0]
-        AB = np.empty((n, 21, 14), np.float32); qdd = np.empty((n, 7), np.float32)
+        AB = np.empty((n, self.n + self.m, self.n), np.float32); qdd = np.empty((n, self.npos), np.float32)
         self._ck(self.L.pddp_unit_integrator_gradient(self.h, px, pu, n, AB.ctypes.data_as(FP), qdd.ctypes.data_as(FP)), "pddp_unit_integrator_gradient")
         return AB, qdd
+
+    def integrator(self, x, u):
+        """x_{k+1} = _integrator(x_k, u_k) of the configured INTEGRATOR (plug-in plants)"""
+        x, px = _f(x); u, pu = _f(u); n = x.shape[0]
+        xn = np.empty((n, self.n), np.float32)
+        self._ck(self.L.pddp_unit_integrator(self.h, px, pu, n, xn.ctypes.data_as(FP)), "pddp_unit_integrator")
+        return xn
+
+    def cost(self, x, u, xGoal, knot):
+        """costFunc and costGrad of a plug-in plant on n samples: returns (J [n], H [n, n+m, n+m], g [n, n+m])"""
+        x, px = _f(x); u, pu = _f(u); xg, pg = _f(xGoal); n = x.shape[0]; nm = self.n + self.m
+        kn = np.ascontiguousarray(np.broadcast_to(knot, (n,)), dtype=np.int32)
+        J = np.empty(n, np.float32); H = np.empty((n, nm, nm), np.float32); g = np.empty((n, nm), np.float32)
+        self._ck(self.L.pddp_unit_cost(self.h, px, pu, pg, kn.ctypes.data_as(IP), n, J.ctypes.data_as(FP), H.ctypes.data_as(FP), g.ctypes.data_as(FP)), "pddp_unit_cost")
+        return J, H, g
 
     # ---- phase-level access -------------------------------------------------------------------------------------
     def get(self, name):
@@ -283,7 +345,7 @@ class Solver:
 
     def load_init(self, x0, u0, xGoal, ignoreFirstDefectFlag=1):
         B, N = self.cfg.batch, self.cfg.N
-        x0, px = _f(np.broadcast_to(x0, (B, N, 14))); u0, pu = _f(np.broadcast_to(u0, (B, N, 7))); xg, pg = _f(np.broadcast_to(xGoal, (B, 14)))
+        x0, px = _f(np.broadcast_to(x0, (B, N, self.n))); u0, pu = _f(np.broadcast_to(u0, (B, N, self.m))); xg, pg = _f(np.broadcast_to(xGoal, (B, self.n)))
         self._ck(self.L.pddp_phase_load_init(self.h, px, pu, pg, ignoreFirstDefectFlag), "load_init")
 
     def backwardPassGPU(self):

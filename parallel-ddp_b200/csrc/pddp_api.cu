@@ -2,10 +2,13 @@
 // The host code is C++ (the reference is compiled C++/CUDA); there is no CPU fallback: every entry point fails
 // with PDDP_E_NODEVICE / PDDP_E_CUDA when no device can run the kernels.
 #include "../../include/pddp.h"
+#include "../../include/pddp_plant.h"
 #include "kernels.cuh"
 #include "kuka_model_data.inc"
 
 #include <cmath>
+#include <dlfcn.h>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -26,7 +29,7 @@ struct pddp_solver {
     int groups = 1;
     std::vector<void*> allocs;
     std::string err;
-    int cur = 0;                       // Pbuf[cur] is "P" (latest), Pbuf[cur^1] is "Pp"
+    const pddp_plant_ops *ops = nullptr;    // plug-in plant (PLANT 1-3 and registered ones); null = the Kuka kernels of kernels.cuh
     float *w_KT = nullptr, *w_P = nullptr, *w_p = nullptr, *w_d = nullptr;     // warm-start inputs (pddp_set_warm_start)
     bool skip_env = false;
     int next_clear = 1, next_rollout = 0;                                      // loadVarsGPU flags of the next solve
@@ -62,6 +65,72 @@ extern "C" void pddp_default_config_kuka(pddp_config *c, int N, int batch){
     c->Q_xdEE = (float)0.1; c->QF_xdEE = (float)1000.0; c->Q_xEE = 0.f; c->QF_xEE = 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------- plant plug-ins
+// Pendulum, cart-pole and quadrotor are plant translation units (plant_tu.cu) linked into this library; further plants arrive
+// through pddp_register_plant / pddp_load_plant_library.  The Kuka arm (PLANT 4) keeps its own kernels (kernels.cuh).
+extern "C" const pddp_plant_ops *pddp_plant_entry_1(void);
+extern "C" const pddp_plant_ops *pddp_plant_entry_2(void);
+extern "C" const pddp_plant_ops *pddp_plant_entry_3(void);
+namespace {
+constexpr int MAX_PLANTS = 64;
+const pddp_plant_ops *g_plants[MAX_PLANTS] = {nullptr};
+std::mutex g_plants_mutex;
+std::string g_plant_error;
+bool plant_ops_ok(const pddp_plant_ops *o){
+    return o && o->abi == PDDP_PLANT_ABI && o->state_size_bytes == sizeof(DevState) && o->mpc_size_bytes == sizeof(MpcState) &&
+           o->plant_id >= 1 && o->plant_id < MAX_PLANTS && o->plant_id != PDDP_PLANT_KUKA && o->state_size == 2*o->num_pos &&
+           o->state_size <= 32 && o->control_size >= 1 && o->control_size <= 32 && o->launch_bp && o->launch_sim && o->launch_nis;
+}
+const pddp_plant_ops *find_plant(int id){
+    std::lock_guard<std::mutex> lk(g_plants_mutex);
+    if (!g_plants[1]){ g_plants[1] = pddp_plant_entry_1(); g_plants[2] = pddp_plant_entry_2(); g_plants[3] = pddp_plant_entry_3(); }
+    return (id >= 1 && id < MAX_PLANTS) ? g_plants[id] : nullptr;
+}
+}
+extern "C" int pddp_register_plant(const pddp_plant_ops *ops){
+    if (!plant_ops_ok(ops)){ g_plant_error = "plant table rejected: ABI / struct size / dimensions do not match this libpddp"; return PDDP_E_INVALID; }
+    find_plant(0);
+    std::lock_guard<std::mutex> lk(g_plants_mutex);
+    g_plants[ops->plant_id] = ops;
+    return 0;
+}
+extern "C" int pddp_load_plant_library(const char *path){
+    if (!path){ return PDDP_E_INVALID; }
+    void *lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib){ g_plant_error = std::string("dlopen: ") + dlerror(); return PDDP_E_INVALID; }
+    pddp_plant_entry_fn fn = reinterpret_cast<pddp_plant_entry_fn>(dlsym(lib, "pddp_plant_entry"));
+    if (!fn){ g_plant_error = "the library does not export pddp_plant_entry"; dlclose(lib); return PDDP_E_INVALID; }
+    const int rc = pddp_register_plant(fn());
+    return rc ? rc : fn()->plant_id;
+}
+extern "C" const char *pddp_plant_error(void){ return g_plant_error.c_str(); }
+extern "C" int pddp_plant_dims(int plant, int *num_pos, int *state_size, int *control_size){
+    int np = 7, n = 14, m = 7;
+    if (plant != PDDP_PLANT_KUKA){ const pddp_plant_ops *o = find_plant(plant); if (!o){ return PDDP_E_INVALID; } np = o->num_pos; n = o->state_size; m = o->control_size; }
+    if (num_pos){ *num_pos = np; } if (state_size){ *state_size = n; } if (control_size){ *control_size = m; }
+    return 0;
+}
+
+// config.cuh:21-136 per PLANT, with the cost weights of plants/cost_{pend,cart,quad}.cuh (the pendulum's velocity weight falls through
+// QR(i) to R = 0.1; the cart-pole has its own set for N = 512) and the WAFR example's for the arm
+extern "C" int pddp_default_config(pddp_config *c, int plant, int N, int batch){
+    if (!c){ return PDDP_E_INVALID; }
+    if (plant == PDDP_PLANT_KUKA){ pddp_default_config_kuka(c, N, batch); return 0; }
+    if (plant < PDDP_PLANT_PEND || plant > PDDP_PLANT_QUAD){ return PDDP_E_INVALID; }
+    std::memset(c, 0, sizeof(*c));
+    c->plant = plant; c->N = N; c->M = 4; c->max_iter = 100; c->batch = batch; c->device = 0; c->integrator = 3;
+    c->n_alpha = 32; c->alpha_base = 0.75f; c->total_time = 4.0f;
+    c->rho_min = (float)0.01; c->rho_max = (float)10000000.0; c->rho_factor = (float)1.25;
+    c->exp_red_min = (float)0.05; c->exp_red_max = (float)1.25; c->max_defect = (float)1.0; c->tol_cost = 0.0f;
+    if (plant == PDDP_PLANT_PEND){ c->rho_init = (float)10.0; c->Q1 = (float)1.0; c->Q2 = (float)0.1; c->R = (float)0.1; c->QF1 = c->QF2 = (float)1000.0; }
+    else if (plant == PDDP_PLANT_CART){
+        c->rho_init = (float)10.0; c->max_defect = (float)0.75;
+        if (N == 512){ c->Q1 = (float)0.01; c->Q2 = (float)0.01; c->R = (float)0.001; c->QF1 = c->QF2 = (float)100000.0; }
+        else { c->Q1 = (float)0.01; c->Q2 = (float)0.001; c->R = (float)0.0001; c->QF1 = c->QF2 = (float)1000.0; }
+    } else { c->rho_init = (float)1.0; c->n_alpha = 16; c->alpha_base = 0.5f; c->Q1 = (float)0.01; c->Q2 = (float)0.001; c->R = (float)5.0; c->QF1 = c->QF2 = (float)1000.0; }
+    return 0;
+}
+
 extern "C" const char *pddp_last_error(pddp_handle h){ return h ? h->err.c_str() : g_create_error.c_str(); }
 
 template <typename T>
@@ -77,8 +146,11 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     *out = nullptr;
     auto fail = [&](const std::string &msg, int code){ g_create_error = msg; return code; };
     if (!cfg){ return fail("null config", PDDP_E_INVALID); }
-    if (cfg->plant != PDDP_PLANT_KUKA){ return fail("only PLANT 4 (Kuka iiwa14) has device kernels in this build", PDDP_E_INVALID); }
-    if (cfg->integrator != 1){ return fail("only the Euler integrator (INTEGRATOR 1, the Kuka default) is built", PDDP_E_INVALID); }
+    const pddp_plant_ops *ops = (cfg->plant == PDDP_PLANT_KUKA) ? nullptr : find_plant(cfg->plant);
+    if (cfg->plant != PDDP_PLANT_KUKA && !ops){ return fail("unknown PLANT: 1 pendulum, 2 cart-pole, 3 quadrotor, 4 Kuka iiwa14, or one registered with pddp_register_plant", PDDP_E_INVALID); }
+    if (!ops && cfg->integrator != 1){ return fail("the Kuka kernels are built for the Euler integrator (INTEGRATOR 1, config.cuh:58)", PDDP_E_INVALID); }
+    if (ops && (cfg->integrator < 1 || cfg->integrator > 3)){ return fail("INTEGRATOR must be 1 (Euler), 2 (Midpoint) or 3 (RK3)", PDDP_E_INVALID); }
+    if (ops && cfg->ee_cost){ return fail("EE_COST needs an end effector: PLANT 4 only (cost_pend.cuh:9-10)", PDDP_E_INVALID); }
     if (cfg->N < 32 || cfg->N > 1024 || (cfg->N & (cfg->N-1))){ return fail("N must be a power of two in [32,1024]", PDDP_E_INVALID); }
     if (cfg->M < 1 || cfg->M > 8 || cfg->N % cfg->M){ return fail("M must divide N and be <= 8", PDDP_E_INVALID); }
     if (cfg->n_alpha < 1 || cfg->n_alpha > PDDP_MAX_ALPHA){ return fail("n_alpha out of range", PDDP_E_INVALID); }
@@ -87,8 +159,9 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0){ cudaGetLastError(); return fail("no CUDA device (this library has no CPU path)", PDDP_E_NODEVICE); }
     if (cfg->device < 0 || cfg->device >= ndev){ return fail("bad device ordinal", PDDP_E_INVALID); }
     pddp_handle h = new pddp_solver();
-    h->cfg = *cfg; h->n = kuka::NX; h->m = kuka::NU;
-    auto bail = [&](int code){ g_create_error = h->err; for (void *p : h->allocs){ cudaFree(p); } delete h; return code; };
+    for (auto &e : h->ev){ e = nullptr; }
+    h->cfg = *cfg; h->ops = ops; h->n = ops ? ops->state_size : kuka::NX; h->m = ops ? ops->control_size : kuka::NU;
+    auto bail = [&](int code){ g_create_error = h->err; pddp_destroy(h); return code; };      // the same cleanup as a live handle: streams, events, pinned and device memory
     #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess){ h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return bail(PDDP_E_CUDA); } } while (0)
     CKC(cudaSetDevice(cfg->device));
     { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && sms > 0){ h->num_sms = sms; } }
@@ -102,6 +175,8 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     DevState &S = h->S; std::memset(&S, 0, sizeof(S)); S.skip_unchanged = h->skip_env ? 1 : 0;
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
     S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter; S.iter_cap = cfg->max_iter;
+    S.npos = ops ? ops->num_pos : kuka::NB; S.integrator = cfg->integrator;
+    S.ab_stride = ops ? n*(n+m) : AB_STRIDE; S.h_stride = ops ? (n+m)*(n+m) : H_STRIDE; S.g_stride = ops ? (n+m) : G_STRIDE;
     S.dt = (float)((double)cfg->total_time/(double)(N-1));          // (T)TIME_STEP, config.cuh:136
     S.tol_cost = cfg->tol_cost; S.two_tol = (float)(2*(double)cfg->tol_cost);
     S.rho_min = cfg->rho_min; S.rho_max = cfg->rho_max; S.rho_factor = cfg->rho_factor; S.inv_rho_factor = (float)(1.0/(double)cfg->rho_factor);
@@ -112,16 +187,23 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.Q_xdEE = cfg->Q_xdEE; S.QF_xdEE = cfg->QF_xdEE; S.Q_xEE = cfg->Q_xEE; S.QF_xEE = cfg->QF_xEE;
     float *dI, *dTb, *dal;
     #define DA(ptr, count, name) do { if (dalloc(h, &(ptr), (size_t)(count), name)){ return bail(PDDP_E_CUDA); } } while (0)
-    DA(dI, 252, nullptr); DA(dTb, 252, nullptr); DA(dal, PDDP_MAX_ALPHA, nullptr);
+    const size_t model_floats = ops ? (size_t)36*ops->num_pos : 252;
+    DA(dI, model_floats, nullptr); DA(dTb, model_floats, nullptr); DA(dal, PDDP_MAX_ALPHA, nullptr);
     std::vector<float> al(PDDP_MAX_ALPHA, 0.f);
     for (int i = 0; i < A; i++){ al[i] = (float)std::pow((double)cfg->alpha_base, i); }    // nisInitHelpers.cuh:829
-    CKC(cudaMemcpy(dI, KUKA_I_DATA, sizeof(KUKA_I_DATA), cudaMemcpyHostToDevice));
-    CKC(cudaMemcpy(dTb, KUKA_TBODY_DATA, sizeof(KUKA_TBODY_DATA), cudaMemcpyHostToDevice));
+    if (ops){
+        std::vector<float> hI(model_floats, 0.f), hT(model_floats, 0.f);
+        if (ops->init_model){ ops->init_model(hI.data(), hT.data()); }                   // initI / initT of the plant header
+        CKC(cudaMemcpy(dI, hI.data(), model_floats*4, cudaMemcpyHostToDevice)); CKC(cudaMemcpy(dTb, hT.data(), model_floats*4, cudaMemcpyHostToDevice));
+    } else {
+        CKC(cudaMemcpy(dI, KUKA_I_DATA, sizeof(KUKA_I_DATA), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(dTb, KUKA_TBODY_DATA, sizeof(KUKA_TBODY_DATA), cudaMemcpyHostToDevice));
+    }
     CKC(cudaMemcpy(dal, al.data(), al.size()*sizeof(float), cudaMemcpyHostToDevice));
     S.I = dI; S.Tbody = dTb; S.alpha = dal;
     DA(S.x, (size_t)B*A*N*n, "x"); DA(S.u, (size_t)B*A*N*m, "u"); DA(S.d, (size_t)B*A*N*n, "d");
     DA(S.xp, (size_t)B*N*n, "xp"); DA(S.xp2, (size_t)B*N*n, "xp2"); DA(S.up, (size_t)B*N*m, "up"); DA(S.dp, (size_t)B*N*n, "dp");
-    DA(S.AB, (size_t)B*N*AB_STRIDE, nullptr); DA(S.H, (size_t)B*N*H_STRIDE, nullptr); DA(S.g, (size_t)B*N*G_STRIDE, nullptr);
+    DA(S.AB, (size_t)B*N*S.ab_stride, nullptr); DA(S.H, (size_t)B*N*S.h_stride, nullptr); DA(S.g, (size_t)B*N*S.g_stride, nullptr);
     DA(S.Pbuf[0], (size_t)B*N*n*n, nullptr); DA(S.Pbuf[1], (size_t)B*N*n*n, nullptr); DA(S.pbuf[0], (size_t)B*N*n, nullptr); DA(S.pbuf[1], (size_t)B*N*n, nullptr);
     DA(S.KT, (size_t)B*N*n*m, "KT"); DA(S.du, (size_t)B*N*m, "du"); DA(S.ApBK, (size_t)B*N*n*n, "ApBK"); DA(S.Bdu, (size_t)B*N*n, "Bdu");
     DA(S.xGoal, (size_t)B*n, "xGoal"); DA(S.costk, (size_t)B*A*N, "costk");
@@ -138,26 +220,30 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     CKC(cudaMallocHost((void**)&h->h_stage, h->h_stage_bytes));
     CKC(cudaMallocHost((void**)&h->h_nactive, sizeof(int)));
     // dynamic shared memory of each kernel
-    h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
-    h->smem_sweep = SWEEP_SLOTS*sizeof(SweepSlot<kuka::NX>);
-    h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
     h->smem_sel = ((size_t)A*N + 2*A)*sizeof(float);
-    h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
-    h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
-    h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
-    CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
-    CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
-    CKC(cudaFuncSetAttribute(sim_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
-    CKC(cudaFuncSetAttribute(sim_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
-    CKC(cudaFuncSetAttribute(sim_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
-    CKC(cudaFuncSetAttribute(sim_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
-    // latency shape of the simulation when one warp per (interval, candidate) of the WHOLE batch still leaves a scheduler per warp
-    { const char *env = std::getenv("PDDP_SIM_LANES"); const int v = env ? std::atoi(env) : 0;
-      h->sim_lanes = (v == 16 || v == 32) ? v : (((long long)B*A*M <= 4LL*h->num_sms) ? 32 : 16); }
     CKC(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sel));
-    CKC(cudaFuncSetAttribute(nis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nis));
-    CKC(cudaFuncSetAttribute(unit_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_udyn));
-    CKC(cudaFuncSetAttribute(unit_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ugrad));
+    if (ops){
+        if (ops->prepare){ const int rc = ops->prepare(M); if (rc){ h->err = std::string("plant prepare: ") + cudaGetErrorString((cudaError_t)rc); return bail(PDDP_E_CUDA); } }
+    } else {
+        h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
+        h->smem_sweep = SWEEP_SLOTS*sizeof(SweepSlot<kuka::NX>);
+        h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
+        h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
+        h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
+        h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
+        CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
+        CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
+        CKC(cudaFuncSetAttribute(sim_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+        CKC(cudaFuncSetAttribute(sim_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+        CKC(cudaFuncSetAttribute(sim_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+        CKC(cudaFuncSetAttribute(sim_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
+        // latency shape of the simulation when one warp per (interval, candidate) of the WHOLE batch still leaves a scheduler per warp
+        { const char *env = std::getenv("PDDP_SIM_LANES"); const int v = env ? std::atoi(env) : 0;
+          h->sim_lanes = (v == 16 || v == 32) ? v : (((long long)B*A*M <= 4LL*h->num_sms) ? 32 : 16); }
+        CKC(cudaFuncSetAttribute(nis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nis));
+        CKC(cudaFuncSetAttribute(unit_dynamics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_udyn));
+        CKC(cudaFuncSetAttribute(unit_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_ugrad));
+    }
     CKC(cudaDeviceSynchronize());
     *out = h;
     return 0;
@@ -166,10 +252,10 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
 extern "C" void pddp_destroy(pddp_handle h){
     if (!h){ return; }
     cudaSetDevice(h->cfg.device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream){ cudaStreamSynchronize(h->stream); }
     for (void *p : h->allocs){ cudaFree(p); }
     if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
-    for (auto &e : h->ev){ cudaEventDestroy(e); }
+    for (auto &e : h->ev){ if (e){ cudaEventDestroy(e); } }
     for (auto &e : h->gev){ cudaEventDestroy(e); }
     for (auto st : h->gstreams){ cudaStreamDestroy(st); }
     delete h;
@@ -208,13 +294,15 @@ static int launch_reset(pddp_handle h, int ignore_first, int clear){
     CK(cudaMemsetAsync(S.du, 0, (size_t)B*N*m*4, h->stream));
     CK(cudaMemsetAsync(S.dT, 0, (size_t)B*A*4, h->stream));
     reset_kernel<<<B, 128, 0, h->stream>>>(S, h->cfg.rho_init, ignore_first);
-    h->cur = 0; h->launches += 1;
+    h->launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
+#define CKP(call) do { const int e_ = (call); if (e_){ h->err = std::string(#call) + ": " + cudaGetErrorString((cudaError_t)e_); return PDDP_E_CUDA; } } while (0)
 // forward simulation of n_cand candidates of problems [b0, b0+nb): cost variant and lane shape picked here
 static void launch_sim_any(pddp_handle h, cudaStream_t st, int b0, int nb, int n_cand){
-    DevState &S = h->S; const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw), cta = 32*S.M;
+    DevState &S = h->S;
+    if (h->ops){ h->ops->launch_sim(&S, st, b0, nb, n_cand); return; } const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw), cta = 32*S.M;
     if (h->sim_lanes == 32){
         if (S.ee){ sim_kernel<true, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); } else { sim_kernel<false, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); }
     } else {
@@ -231,9 +319,12 @@ static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInit
         launch_sim_any(h, h->stream, 0, B, 1);
         h->launches += 1;
     }
+    if (h->ops){ CKP(h->ops->launch_nis(&S, h->stream, rollout ? 2 : 1, 0, S.B)); CKP(h->ops->launch_init_cost(&S, h->stream)); h->launches += 1; }
+    else {
     nis_kernel<<<(S.B*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, h->stream>>>(S, rollout ? 2 : 1, 1, 0, S.B);
     // end-effector cost: the initial per-knot costs come from nis_kernel (they need the tool pose), or from the rollout's partials
     if (!S.ee){ init_cost_kernel<<<S.B, S.N, 0, h->stream>>>(S); h->launches += 1; }
+    }
     select_kernel<<<S.B, 32*S.A, h->smem_sel, h->stream>>>(S, 1, 0);
     h->launches += 2;
     CK(cudaGetLastError());
@@ -242,11 +333,13 @@ static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInit
 // problems [b0, b0+nb) on stream st
 static int launch_bp(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_CTA, h->smem_bp, st>>>(S, h->cur, b0);
+    if (h->ops){ CKP(h->ops->launch_bp(&S, st, b0, nb)); h->launches += 1; return 0; }
+    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_CTA, h->smem_bp, st>>>(S, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S; if (S.M == 1){ return 0; }
+    if (h->ops){ CKP(h->ops->launch_sweep(&S, st, b0, nb, h->num_sms)); h->launches += 1; return 0; }
     // enough CTAs to cover the SMs: split the step sizes of one problem over up to A CTAs (power-of-two divisor of A)
     int splits = 1; while (nb*splits*2 <= h->num_sms && (S.A % (splits*2)) == 0){ splits *= 2; }
     sweep_kernel<kuka::NX><<<nb*splits, 32*(S.A/splits), h->smem_sweep, st>>>(S, splits, b0);
@@ -264,6 +357,7 @@ static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
 }
 static int launch_nis(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
+    if (h->ops){ CKP(h->ops->launch_nis(&S, st, 0, b0, nb)); h->launches += 1; return 0; }
     nis_kernel<<<(nb*S.N + NIS_WARPS*(32/NIS_LANES) - 1)/(NIS_WARPS*(32/NIS_LANES)), 32*NIS_WARPS, h->smem_nis, st>>>(S, 0, 0, b0, nb);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
@@ -281,7 +375,6 @@ static int run_iterations(pddp_handle h, double *times_ms, int groups){
     if (groups > 1){ CK(cudaEventRecord(h->gev[8], h->stream)); for (int g = 1; g < groups; g++){ CK(cudaStreamWaitEvent(h->gstreams[g], h->gev[8], 0)); } }
     int it_done = 0;
     for (int it = 0; it < S.iter_cap; it++){
-        h->cur ^= 1;
         for (int g = 0; g < groups; g++){
             const int b0 = (int)((long)S.B*g/groups), nb = (int)((long)S.B*(g+1)/groups) - b0; cudaStream_t st = h->gstreams[g]; int rc;
             mark(); if ((rc = launch_bp(h, st, b0, nb))){ return rc; }
@@ -422,8 +515,10 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
         h->d_xActual = xa; h->mpc.xActual = xa;
         void *q = nullptr; CK(cudaMalloc(&q, 3*B*sizeof(int))); h->d_mpc_flags = (int*)q; h->allocs.push_back(q);
         h->mpc.shift = h->d_mpc_flags; h->mpc.clear = h->d_mpc_flags + B;
-        h->smem_mpc = 2*36*kuka::NB*sizeof(float) + sizeof(SimGroupSmem);
-        CK(cudaFuncSetAttribute(mpc_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_mpc));
+        if (!h->ops){
+            h->smem_mpc = 2*36*kuka::NB*sizeof(float) + sizeof(SimGroupSmem);
+            CK(cudaFuncSetAttribute(mpc_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_mpc));
+        }
     }
     // the state runiLQR_MPC_GPU expects to find (LCMHelpers.cuh:224-233 + the caller's set-up): the plan in the current slot and in
     // xp/up, everything else zero
@@ -437,7 +532,8 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
     CK(cudaMemsetAsync(h->mpc.x_old, 0, B*N*n*4, h->stream)); CK(cudaMemsetAsync(h->mpc.u_old, 0, B*N*m*4, h->stream)); CK(cudaMemsetAsync(h->mpc.KT_old, 0, B*N*n*m*4, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemset(S.alphaIndex, 0, B*sizeof(int)));                 // the plan starts in slot 0 (MPCHelpers.cuh:236)
-    h->mpc_lss.assign(B, 0); h->mpc_ready = true; h->cur = 0;
+    CK(cudaMemset(S.iter, 0, B*sizeof(int)));                       // both cost-to-go buffers are zero: no roles to keep yet
+    h->mpc_lss.assign(B, 0); h->mpc_ready = true;
     return 0;
 }
 
@@ -461,16 +557,15 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     CK(cudaMemcpyAsync(h->d_xActual, xActual, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.xGoal, xGoal, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
     // loadVarsGPU_MPC + hand-over; the cost-to-go buffers keep their roles: the first backward pass must seed its blocks from the
-    // shifted Pp (the older buffer) and overwrite P (the newer one), so the flip that precedes it has to land on the newer buffer
-    mpc_load_kernel<<<B, 256, h->smem_mpc, h->stream>>>(S, h->mpc, h->cur);
+    // shifted Pp (the older buffer) and overwrite P (the newer one) -- the load kernel puts them into the slots that the restarted
+    // iteration counter selects, per problem (problems that stopped at different iterations have different parities)
+    if (h->ops){ CKP(h->ops->launch_mpc_load(&S, &h->mpc, h->stream)); }
+    else { mpc_load_kernel<<<B, 256, h->smem_mpc, h->stream>>>(S, h->mpc); }
     h->launches += 1; CK(cudaGetLastError());
-    const int cur_keep = h->cur ^ 1;
     reset_kernel<<<B, 128, 0, h->stream>>>(S, h->cfg.rho_init, ignoreFirstDefectFlag);
     h->launches += 1; CK(cudaGetLastError());
-    h->cur = cur_keep;
-    if ((rc = launch_init(h, 0))){ return rc; }
-    S.iter_cap = max_iter;
-    rc = run_iterations(h, nullptr, 1);
+    rc = launch_init(h, 0);
+    if (!rc){ S.iter_cap = max_iter; rc = run_iterations(h, nullptr, 1); }
     S.iter_cap = S.max_iter; S.cost_shift = nullptr;
     if (rc){ return rc; }
     // success bookkeeping (MPCHelpers.cuh:987-991, 757-758) needs the step-size trace on the host
@@ -493,11 +588,17 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     CK(cudaMemcpyAsync(sx, h->d_xout, (size_t)B*N*n*4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(su, h->d_uout, (size_t)B*N*m*4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    std::vector<float> kt((size_t)N*n*m);
+    // gains of the successful problems: runs of consecutive successes travel in one copy each (all of them in one when every solve took a step)
+    for (int b = 0; b < B; ){
+        if (!flags[2*(size_t)B + b]){ b++; continue; }
+        int e = b; while (e < B && flags[2*(size_t)B + e]){ e++; }
+        CK(cudaMemcpyAsync(KT + (size_t)b*N*n*m, dKT + (size_t)b*N*n*m, (size_t)(e - b)*N*n*m*4, cudaMemcpyDeviceToHost, h->stream));
+        b = e;
+    }
+    CK(cudaStreamSynchronize(h->stream));
     for (int b = 0; b < B; b++){
         if (flags[2*(size_t)B + b]){
             std::memcpy(x + (size_t)b*N*n, sx + (size_t)b*N*n, (size_t)N*n*4); std::memcpy(u + (size_t)b*N*m, su + (size_t)b*N*m, (size_t)N*m*4);
-            CK(cudaMemcpy(KT + (size_t)b*N*n*m, dKT + (size_t)b*N*n*m, (size_t)N*n*m*4, cudaMemcpyDeviceToHost));
         }
         if (last_successful_solve){ last_successful_solve[b] = h->mpc_lss[b]; }
         if (iters_out){ iters_out[b] = its[b]; }
@@ -658,54 +759,124 @@ extern "C" int pddp_make_inputs_kuka(int N, int batch, unsigned seed0, float *x0
     return 0;
 }
 
+// initial guesses and goals of the reference's example for the other plants (WAFR_iLQR_examples.cu:19-33,72-78,87-90,110-115): one
+// std::default_random_engine(seed) per problem, draws in knot order then state order -- the deterministic harness' inputs
+extern "C" int pddp_make_inputs(int plant, int N, int batch, unsigned seed0, float *x0, float *u0, float *xGoal){
+    if (plant == PDDP_PLANT_KUKA){ return pddp_make_inputs_kuka(N, batch, seed0, x0, u0, xGoal); }
+    if (plant < PDDP_PLANT_PEND || plant > PDDP_PLANT_QUAD || !x0 || !u0 || !xGoal){ return PDDP_E_INVALID; }
+    const int n = plant == PDDP_PLANT_PEND ? 2 : (plant == PDDP_PLANT_CART ? 4 : 12), m = plant == PDDP_PLANT_QUAD ? 4 : 1, np = n/2;
+    for (int b = 0; b < batch; b++){
+        std::default_random_engine eng(seed0 + b);
+        std::normal_distribution<double> dist(0.0, 0.001);
+        for (int k = 0; k < N; k++){
+            float *xk = x0 + ((size_t)b*N + k)*n;
+            if (plant == PDDP_PLANT_PEND){ xk[0] = 0.0f; xk[1] = static_cast<float>(dist(eng)); }
+            else if (plant == PDDP_PLANT_CART){ xk[0] = 0.0f; xk[1] = 0.0f; xk[2] = static_cast<float>(dist(eng)); xk[3] = static_cast<float>(dist(eng)); }
+            else { for (int i = 0; i < n; i++){ xk[i] = (i == 2) ? 0.5f : (i >= np ? static_cast<float>(dist(eng)) : 0.0f); } }
+        }
+        for (int k = 0; k < N; k++){ float *uk = u0 + ((size_t)b*N + k)*m; for (int i = 0; i < m; i++){ uk[i] = plant == PDDP_PLANT_QUAD ? (float)1.22625 : (float)0.01; } }
+        float *g = xGoal + (size_t)b*n; for (int i = 0; i < n; i++){ g[i] = 0.0f; }
+        if (plant == PDDP_PLANT_PEND){ g[0] = (float)3.1416; } else if (plant == PDDP_PLANT_CART){ g[1] = (float)3.1416; } else { g[0] = 7.0f; g[1] = 10.0f; g[2] = 0.5f; }
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------- plug-in unit calls
+namespace {
+// scratch device buffers of one unit call, released on every path out of it
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch(){ for (void *p : ptrs){ cudaFree(p); } }
+    template <typename T> T *get(size_t count){ void *p = nullptr; if (cudaMalloc(&p, (count ? count : 1)*sizeof(T)) != cudaSuccess){ return nullptr; } ptrs.push_back(p); return static_cast<T*>(p); }
+};
+}
 extern "C" int pddp_unit_dynamics(pddp_handle h, const float *x, const float *u, int nsamp, float *qdd){
-    if (!h || nsamp < 1){ return PDDP_E_INVALID; }
+    if (!h || nsamp < 1 || !x || !u || !qdd){ return PDDP_E_INVALID; }
     CK(cudaSetDevice(h->cfg.device));
-    float *dx, *du, *dq;
-    CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4));
-    CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
-    unit_dynamics_kernel<<<nsamp < 1184 ? nsamp : 1184, 32, h->smem_udyn, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, dq);
+    const size_t n = h->S.n, m = h->S.m, np = h->S.npos; Scratch sc;
+    float *dx = sc.get<float>(nsamp*n), *du = sc.get<float>(nsamp*m), *dq = sc.get<float>(nsamp*np);
+    if (!dx || !du || !dq){ h->err = "cudaMalloc failed (unit call)"; return PDDP_E_CUDA; }
+    CK(cudaMemcpy(dx, x, nsamp*n*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, nsamp*m*4, cudaMemcpyHostToDevice));
+    if (h->ops){ CKP(h->ops->unit_dynamics(&h->S, h->stream, dx, du, nsamp, dq)); }
+    else { unit_dynamics_kernel<<<nsamp < 1184 ? nsamp : 1184, 32, h->smem_udyn, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, dq); }
     CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(du); cudaFree(dq);
+    CK(cudaMemcpy(qdd, dq, nsamp*np*4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+static int unit_gradient_impl(pddp_handle h, const float *x, const float *u, int nsamp, float *AB, float *qdd, float *xnext){
+    if (!h || nsamp < 1 || !x || !u){ return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    const size_t n = h->S.n, m = h->S.m, np = h->S.npos, nab = n*(n+m); Scratch sc;
+    float *dx = sc.get<float>(nsamp*n), *du = sc.get<float>(nsamp*m), *dq = sc.get<float>(nsamp*np), *dab = sc.get<float>(nsamp*nab), *dxn = sc.get<float>(nsamp*n);
+    if (!dx || !du || !dq || !dab || !dxn){ h->err = "cudaMalloc failed (unit call)"; return PDDP_E_CUDA; }
+    CK(cudaMemcpy(dx, x, nsamp*n*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, nsamp*m*4, cudaMemcpyHostToDevice));
+    if (h->ops){ CKP(h->ops->unit_gradient(&h->S, h->stream, dx, du, nsamp, dab, dq, xnext ? dxn : nullptr)); }
+    else {
+        if (xnext){ h->err = "pddp_unit_integrator: plug-in plants only (the Kuka step is covered by the simulation traces)"; return PDDP_E_INVALID; }
+        unit_gradient_kernel<<<nsamp < 888 ? nsamp : 888, 32, h->smem_ugrad, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, h->S.dt, dab, dq);
+    }
+    CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
+    if (AB){ CK(cudaMemcpy(AB, dab, nsamp*nab*4, cudaMemcpyDeviceToHost)); }
+    if (qdd){ CK(cudaMemcpy(qdd, dq, nsamp*np*4, cudaMemcpyDeviceToHost)); }
+    if (xnext){ CK(cudaMemcpy(xnext, dxn, nsamp*n*4, cudaMemcpyDeviceToHost)); }
     return 0;
 }
 extern "C" int pddp_unit_integrator_gradient(pddp_handle h, const float *x, const float *u, int nsamp, float *AB, float *qdd){
-    if (!h || nsamp < 1){ return PDDP_E_INVALID; }
+    if (!AB){ return PDDP_E_INVALID; }
+    return unit_gradient_impl(h, x, u, nsamp, AB, qdd, nullptr);
+}
+extern "C" int pddp_unit_integrator(pddp_handle h, const float *x, const float *u, int nsamp, float *xnext){
+    if (!xnext){ return PDDP_E_INVALID; }
+    return unit_gradient_impl(h, x, u, nsamp, nullptr, nullptr, xnext);
+}
+extern "C" int pddp_unit_cost(pddp_handle h, const float *x, const float *u, const float *xGoal, const int *knot, int nsamp, float *J, float *H, float *g){
+    if (!h || nsamp < 1 || !x || !u || !xGoal || !knot || !J || !H || !g){ return PDDP_E_INVALID; }
+    if (!h->ops){ h->err = "pddp_unit_cost: plug-in plants only (the Kuka cost is fused into its kernels and covered by the phase traces)"; return PDDP_E_INVALID; }
     CK(cudaSetDevice(h->cfg.device));
-    float *dx, *du, *dq, *dab;
-    CK(cudaMalloc(&dx, (size_t)nsamp*14*4)); CK(cudaMalloc(&du, (size_t)nsamp*7*4)); CK(cudaMalloc(&dq, (size_t)nsamp*7*4)); CK(cudaMalloc(&dab, (size_t)nsamp*294*4));
-    CK(cudaMemcpy(dx, x, (size_t)nsamp*14*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, (size_t)nsamp*7*4, cudaMemcpyHostToDevice));
-    unit_gradient_kernel<<<nsamp < 888 ? nsamp : 888, 32, h->smem_ugrad, h->stream>>>(h->S.I, h->S.Tbody, h->S.grav, dx, du, nsamp, h->S.dt, dab, dq);
-    CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(AB, dab, (size_t)nsamp*294*4, cudaMemcpyDeviceToHost));
-    if (qdd){ CK(cudaMemcpy(qdd, dq, (size_t)nsamp*7*4, cudaMemcpyDeviceToHost)); }
-    cudaFree(dx); cudaFree(du); cudaFree(dq); cudaFree(dab);
+    const size_t n = h->S.n, m = h->S.m, nm = n + m; Scratch sc;
+    float *dx = sc.get<float>(nsamp*n), *du = sc.get<float>(nsamp*m), *dg = sc.get<float>(n), *dJ = sc.get<float>(nsamp), *dH = sc.get<float>(nsamp*nm*nm), *dgr = sc.get<float>(nsamp*nm);
+    int *dk = sc.get<int>(nsamp);
+    if (!dx || !du || !dg || !dJ || !dH || !dgr || !dk){ h->err = "cudaMalloc failed (unit call)"; return PDDP_E_CUDA; }
+    CK(cudaMemcpy(dx, x, nsamp*n*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(du, u, nsamp*m*4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dg, xGoal, n*4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dk, knot, nsamp*sizeof(int), cudaMemcpyHostToDevice));
+    CKP(h->ops->unit_cost(&h->S, h->stream, dx, du, dg, dk, nsamp, dJ, dH, dgr));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(J, dJ, nsamp*4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(H, dH, nsamp*nm*nm*4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(g, dgr, nsamp*nm*4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------- phase-level access
 static bool resolve(pddp_handle h, const char *name, void **p, size_t *bytes){
-    std::string s(name); DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n;
-    if (s == "P"){ *p = S.Pbuf[h->cur]; *bytes = B*N*n*n*4; return true; }
-    if (s == "Pp"){ *p = S.Pbuf[h->cur^1]; *bytes = B*N*n*n*4; return true; }
-    if (s == "p"){ *p = S.pbuf[h->cur]; *bytes = B*N*n*4; return true; }
-    if (s == "pp"){ *p = S.pbuf[h->cur^1]; *bytes = B*N*n*4; return true; }
-    auto it = h->arrays.find(s);
+    auto it = h->arrays.find(name);
     if (it == h->arrays.end()){ return false; }
     *p = it->second.first; *bytes = it->second.second; return true;
 }
+// "P","p" / "Pp","pp": the cost-to-go buffer the backward pass of the problem's current iteration writes / the one it seeds its blocks
+// from (DevState::Pbuf).  The roles are per problem (parity of its iteration counter), so these arrays are gathered problem by problem.
+static int pingpong(pddp_handle h, const char *name, void *host, long nbytes, bool to_device){
+    const std::string s(name); DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n;
+    const bool mat = (s == "P" || s == "Pp"), older = (s == "Pp" || s == "pp"); const size_t per = (mat ? N*n*n : N*n)*4;
+    if ((size_t)nbytes != B*per){ h->err = std::string("bad array size: ") + name; return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device)); for (auto st : h->gstreams){ CK(cudaStreamSynchronize(st)); }
+    std::vector<int> it(B); CK(cudaMemcpy(it.data(), S.iter, B*sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; b++){
+        const int idx = (it[b] & 1) ^ (older ? 1 : 0); char *dev = reinterpret_cast<char*>(mat ? S.Pbuf[idx] : S.pbuf[idx]) + b*per, *hp = static_cast<char*>(host) + b*per;
+        if (to_device){ CK(cudaMemcpy(dev, hp, per, cudaMemcpyHostToDevice)); } else { CK(cudaMemcpy(hp, dev, per, cudaMemcpyDeviceToHost)); }
+    }
+    return 0;
+}
+static bool is_pingpong(const char *name){ const std::string s(name); return s == "P" || s == "Pp" || s == "p" || s == "pp"; }
 // AB, H, g live in HBM with padded knot strides (kernels.cuh): the API speaks the reference's dense layout
 static bool padded(pddp_handle h, const char *name, void **p, size_t *tile, size_t *stride){
     std::string s(name); DevState &S = h->S;
-    if (s == "AB"){ *p = S.AB; *tile = (size_t)S.n*(S.n+S.m)*4; *stride = AB_STRIDE*4; return true; }
-    if (s == "H"){ *p = S.H; *tile = (size_t)(S.n+S.m)*(S.n+S.m)*4; *stride = H_STRIDE*4; return true; }
-    if (s == "g"){ *p = S.g; *tile = (size_t)(S.n+S.m)*4; *stride = G_STRIDE*4; return true; }
+    if (s == "AB"){ *p = S.AB; *tile = (size_t)S.n*(S.n+S.m)*4; *stride = (size_t)S.ab_stride*4; return true; }
+    if (s == "H"){ *p = S.H; *tile = (size_t)(S.n+S.m)*(S.n+S.m)*4; *stride = (size_t)S.h_stride*4; return true; }
+    if (s == "g"){ *p = S.g; *tile = (size_t)(S.n+S.m)*4; *stride = (size_t)S.g_stride*4; return true; }
     return false;
 }
 extern "C" int pddp_set_array(pddp_handle h, const char *name, const void *src, long nbytes){
     if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    if (is_pingpong(name)){ return pingpong(h, name, const_cast<void*>(src), nbytes, true); }
     { size_t tile, stride; const size_t rows = (size_t)h->S.B*h->S.N;
       if (padded(h, name, &p, &tile, &stride)){
           if ((size_t)nbytes != tile*rows){ h->err = std::string("bad array size: ") + name; return PDDP_E_INVALID; }
@@ -717,6 +888,7 @@ extern "C" int pddp_set_array(pddp_handle h, const char *name, const void *src, 
 }
 extern "C" int pddp_get_array(pddp_handle h, const char *name, void *dst, long nbytes){
     if (!h){ return PDDP_E_INVALID; } void *p; size_t bytes;
+    if (is_pingpong(name)){ return pingpong(h, name, dst, nbytes, false); }
     { size_t tile, stride; const size_t rows = (size_t)h->S.B*h->S.N;
       if (padded(h, name, &p, &tile, &stride)){
           if ((size_t)nbytes != tile*rows){ h->err = std::string("bad array size: ") + name; return PDDP_E_INVALID; }
@@ -749,7 +921,7 @@ extern "C" int pddp_phase_load_init(pddp_handle h, const float *x0, const float 
         return launch_init(h, rollout);
     });
 }
-extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ h->cur ^= 1; return launch_bp(h, h->stream, 0, h->S.B); }); }
+extern "C" int pddp_phase_backward_pass(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_bp(h, h->stream, 0, h->S.B); }); }
 extern "C" int pddp_phase_forward_sweep(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sweep(h, h->stream, 0, h->S.B); }); }
 extern "C" int pddp_phase_forward_sim(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_sim(h, h->stream, 0, h->S.B); }); }
 extern "C" int pddp_phase_line_search(pddp_handle h){ if (!h){ return PDDP_E_INVALID; } return timed_phase(h, [&](){ return launch_select(h, h->stream, 0, h->S.B); }); }

@@ -18,7 +18,7 @@ template <typename T>
 __host__ __device__ __forceinline__
 T dqdd2dxd(T *dqdd, int r, int c){ return r < NUM_POS ? static_cast<T>(r + NUM_POS == c ? 1 : 0) : dqdd[(c-1)*NUM_POS + r]; }
 
-namespace pddp_plugin {
+namespace pddp_integ {
 // y = a + h*b on both halves of the state: positions advance with `vel`, velocities with `acc`
 template <typename T>
 __host__ __device__ __forceinline__
@@ -39,7 +39,7 @@ void _integrator(T *s_xkp1, T *s_x, T *s_u, T *s_qdd, T *d_I, T *d_Tbody, T dt, 
     if (INTEG == 1){
         dynamics<T>(s_qdd, s_x, s_u, d_I, d_Tbody, s_eePos, 1, s_eeVel);
         hd__syncthreads();
-        pddp_plugin::advance<T>(s_xkp1, s_x, dt, s_x + NUM_POS, s_qdd);
+        pddp_integ::advance<T>(s_xkp1, s_x, dt, s_x + NUM_POS, s_qdd);
     }
     else if (INTEG == 2){
         #ifdef __CUDA_ARCH__
@@ -57,7 +57,7 @@ void _integrator(T *s_xkp1, T *s_x, T *s_u, T *s_qdd, T *d_I, T *d_Tbody, T dt, 
         dynamics<T>(s_qdd, s_mid, s_u, d_I, d_Tbody);
         hd__syncthreads();
         // the positions advance with the INITIAL velocity (integrators.cuh:78), the velocities with the midpoint acceleration
-        pddp_plugin::advance<T>(s_xkp1, s_x, dt, s_x + NUM_POS, s_qdd);
+        pddp_integ::advance<T>(s_xkp1, s_x, dt, s_x + NUM_POS, s_qdd);
     }
     else {
         #ifdef __CUDA_ARCH__

@@ -1,7 +1,9 @@
 // pddp_plugin.cuh -- the plant plug-in surface of libpddp: what a plant author's header may rely on.
 //
 // A plant is a header in the style of the reference's plants/{dynamics,cost}_*.cuh, compiled into its own translation unit
-// (csrc/plant_tu.cu) together with the solver kernels that call it.  It defines
+// (csrc/plant_tu.cu) together with the solver kernels that call it.  plant_tu.cu includes the header INSIDE a namespace of its own
+// (several plants share one library), after <cuda_runtime.h> and <math.h>: a plant header that needs other system headers has them
+// included first with -include.  It defines
 //
 //     NUM_POS, STATE_SIZE, CONTROL_SIZE                                            (config.cuh:21-61)
 //     initI<T>(T *s_I), initT<T>(T *s_T)                                           (dynamics_arm.cuh:71,351; host, 36*NUM_POS floats each)
@@ -30,9 +32,9 @@ __device__ __forceinline__ int &rt_num_time_steps(){ __shared__ int v; return v;
 }
 namespace pddp_plugin { static int host_num_time_steps = 0; }    // host instantiations of plant code (tests only): set by the caller
 #ifdef __CUDA_ARCH__
-#define NUM_TIME_STEPS (pddp_plugin::rt_num_time_steps())
+#define NUM_TIME_STEPS (::pddp_plugin::rt_num_time_steps())
 #else
-#define NUM_TIME_STEPS (pddp_plugin::host_num_time_steps)
+#define NUM_TIME_STEPS (::pddp_plugin::host_num_time_steps)
 #endif
 #ifndef EE_COST
 #define EE_COST 0

@@ -12,11 +12,9 @@
 //   plug_nis_kernel     hand-over + integratorGradientKern + costGradientHessianKern   nisInitHelpers.cuh:203-221,44-93,245-279
 //   plug_mpc_*          loadVarsGPU_MPC incl. rolloutMPC                     MPCHelpers.cuh:602-657,524-556
 // Line search / accept-reject (select_kernel), reset and store kernels are plant independent and live in the main library.
-#pragma once
-#include "../dev_state.cuh"
-#include "../../../include/pddp_plant.h"
-
-namespace pddp {
+//
+// This file has no include guard and no namespace of its own: plant_tu.cu includes it inside the plant's namespace (after
+// dev_state.cuh and include/pddp_plant.h), so that several plants can live in one library.
 
 constexpr int PN = STATE_SIZE, PM = CONTROL_SIZE, PNP = NUM_POS, PNM = STATE_SIZE + CONTROL_SIZE;
 static_assert(PN == 2*PNP, "x = [q ; qd]");
@@ -234,7 +232,7 @@ __global__ void plug_sim_kernel(DevState S, int b0, int n_cand){
     __shared__ float s_x[PN], s_u[PM], s_qdd[PNP], s_xn[PN], s_dx[PN], s_xg[PN];
     const int w = blockIdx.x % S.M, a = (blockIdx.x / S.M) % n_cand, b = b0 + blockIdx.x / (S.M*n_cand), l = plug_tid();
     if (S.done[b]){ return; }
-    if (l == 0){ pddp_plugin::rt_num_time_steps() = S.N; }
+    if (l == 0){ ::pddp_plugin::rt_num_time_steps() = S.N; }
     if (l < n){ s_xg[l] = S.xGoal[b*n + l]; }
     const int N = S.N, NBF = N / S.M, kStart = w*NBF, iters = (w < S.M - 1) ? NBF : NBF - 1;
     const float alpha = S.alpha[a], dt = S.dt;
@@ -280,7 +278,7 @@ __global__ void plug_sim_kernel(DevState S, int b0, int n_cand){
 // per-knot costs of the initial trajectory (initAlgGPU's costKern, nisInitHelpers.cuh:385) into candidate slot 0
 __global__ void plug_init_cost_kernel(DevState S){
     const int b = blockIdx.x, n = PN, m = PM;
-    if (plug_tid() == 0){ pddp_plugin::rt_num_time_steps() = S.N; }
+    if (plug_tid() == 0){ ::pddp_plugin::rt_num_time_steps() = S.N; }
     __syncthreads();
     for (int k = plug_tid(); k < S.N; k += plug_nthreads()){
         S.costk[((size_t)b*S.A + 0)*S.N + k] = costFunc<float>(S.xp + ((size_t)b*S.N + k)*n, S.up + ((size_t)b*S.N + k)*m, S.xGoal + b*n, k, S.Q1, S.Q2, S.R, S.QF1, S.QF2);
@@ -297,7 +295,7 @@ __global__ void plug_nis_kernel(DevState S, int mode, int b0, int nb){
     __shared__ float s_x[PN], s_u[PM], s_qdd[PNP], s_dqdd[PNP*PNM];
     const int N = S.N, b = b0 + blockIdx.x / N, k = blockIdx.x % N, l = plug_tid();
     if (b >= b0 + nb || S.done[b]){ return; }
-    if (l == 0){ pddp_plugin::rt_num_time_steps() = N; }
+    if (l == 0){ ::pddp_plugin::rt_num_time_steps() = N; }
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
     const bool acc = (mode == 2) || ((mode == 0) && S.accepted[b]);
     const int a = S.alphaIndex[b];
@@ -329,7 +327,7 @@ __global__ void plug_mpc_load_kernel(DevState S, MpcState Q){
     constexpr int n = PN, m = PM;
     __shared__ float s_x[PN], s_u[PM], s_qdd[PNP], s_xn[PN];
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b], l = plug_tid(); const bool clear = Q.clear[b] != 0;
-    if (l == 0){ S.init_knot[b] = 0; pddp_plugin::rt_num_time_steps() = N; }
+    if (l == 0){ S.init_knot[b] = 0; ::pddp_plugin::rt_num_time_steps() = N; }
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
     float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     float *P0 = S.Pbuf[0] + (size_t)b*N*n*n, *P1 = S.Pbuf[1] + (size_t)b*N*n*n, *p0 = S.pbuf[0] + (size_t)b*N*n, *p1 = S.pbuf[1] + (size_t)b*N*n;
@@ -396,7 +394,7 @@ __global__ void plug_unit_gradient_kernel(const float *I, const float *Tbody, co
     }
 }
 __global__ void plug_unit_cost_kernel(DevState S, const float *x, const float *u, const float *xg, const int *knot, int nsamp, float *J, float *H, float *g){
-    if (plug_tid() == 0){ pddp_plugin::rt_num_time_steps() = S.N; }
+    if (plug_tid() == 0){ ::pddp_plugin::rt_num_time_steps() = S.N; }
     __syncthreads();
     for (int k = blockIdx.x*plug_nthreads() + plug_tid(); k < nsamp; k += gridDim.x*plug_nthreads()){
         float xs[PN], us[PM];
@@ -467,4 +465,3 @@ static int plug_prepare(int max_M){
     return 0;
 }
 
-} // namespace pddp

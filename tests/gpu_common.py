@@ -12,7 +12,7 @@ pddp = importlib.import_module("parallel-ddp_b200")
 REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
 
 
-def golden(name):
+def golden(name, required=True):
     """tests/golden/<name>.npz, or the raw dump written earlier in the same gpurun call (gpurun_out/golden_raw/<name>.bin)."""
     p = os.path.join(ROOT, "tests", "golden", name + ".npz")
     if os.path.exists(p):
@@ -20,7 +20,9 @@ def golden(name):
     p = os.path.join(ROOT, "gpurun_out", "golden_raw", name + ".bin")
     if os.path.exists(p):
         return refdump.load(p)
-    pytest.skip(f"golden {name} not available")
+    if required:
+        pytest.fail(f"golden fixture {name} is missing: tests/golden/{name}.npz (tests/golden/make_goldens.py) -- a lost fixture must not pass silently")
+    pytest.skip(f"golden {name} not generated yet")
 
 
 def relerr(mine, ref):
