@@ -162,9 +162,19 @@ int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
 
 /* Number of independent problem groups, each iterated on its own CUDA stream so that one group's latency-bound kernels
  * (backward pass, sweep, selection) overlap another group's throughput-bound ones (sim, next-iteration setup).  Results do
- * not depend on it.  Default 4 (env PDDP_GROUPS); the per-phase entries of times_ms are only filled with 1 group.
+ * not depend on it.  Default 4 (env PDDP_GROUPS) for batches of 8 problems or more, else 1; the per-phase entries of times_ms and
+ * pddp_last_iteration_times need 1 group (the phases of different groups overlap, there is no per-phase time then).
  * Returns the value in effect. */
 int pddp_set_groups(pddp_handle h, int groups);
+
+/* Per-iteration device times (ms) of the last pddp_solve* call that was given a times_ms array and ran as ONE problem group
+ * (pddp_set_groups(h, 1); a batch below 8 problems always does): the entries of the reference's simTime / sweepTime / bpTime / nisTime
+ * arrays (DDPWrappers.cuh:60-107).  sim includes the cost / defect reductions and the line search, as in the reference.  Returns the
+ * number of iterations written (<= capacity); any array may be NULL. */
+int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, double *bp_ms, double *nis_ms, int capacity);
+/* max_d of runiLQR_GPU's summary line (DDPWrappers.cuh:134): the largest L1 defect over the shooting-interval boundaries of each
+ * problem's final trajectory, [batch] floats (HOST) */
+int pddp_final_max_defect(pddp_handle h, float *max_d);
 
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);

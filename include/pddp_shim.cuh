@@ -1,33 +1,43 @@
 // pddp_shim.cuh -- source-compatibility shim: the reference's solver-side templates on top of libpddp.so.
 //
-// examples/WAFR_iLQR_examples.cu calls three templates with ~50 raw work pointers each:
-//     allocateMemory_GPU<T>(...)   DDPHelpers/nisInitHelpers.cuh:766-772
-//     runiLQR_GPU<T>(...)          DDPHelpers/DDPWrappers.cuh:8-21
-//     freeMemory_GPU<T>(...)       DDPHelpers/nisInitHelpers.cuh:863-868
-// Including this header INSTEAD of the reference's config.cuh keeps those call sites compiling unchanged (same names,
-// same positional arguments).  The work pointers the reference threads through every call are owned by the library
-// here, so the shim hands back inert placeholders for them and keeps the one thing that matters -- the solver handle --
-// in the slot of `d_x` (the first out-parameter).  x0/u0 are in/out exactly as in the reference (the solution overwrites
-// them, nisInitHelpers.cuh:745-746), Jout/alphaOut need MAX_ITER+1 slots, the six timing outputs are filled from the
-// library's CUDA-event timings, and the one-line summary of DDPWrappers.cuh:134 is printed in the same format.
+// examples/WAFR_iLQR_examples.cu includes ../config.cuh and calls, from its three test drivers,
+//     allocateMemory_GPU<T>(...) / runiLQR_GPU<T>(...) / freeMemory_GPU<T>(...)      testGPU       (nisInitHelpers.cuh:766-772, DDPWrappers.cuh:8-21, nisInitHelpers.cuh:863-868)
+//     allocateMemory_CPU[2]<T> / runiLQR_CPU[2]<T> / freeMemory_CPU[2]<T>            testCPU       (nisInitHelpers.cuh:884-965, DDPWrappers.cuh:140-365)
+//     runSLQ_GPU<T>(...)                                                             testGPU_SLQ   (DDPWrappers.cuh:367)
+// Including this header INSTEAD of ../config.cuh (one changed line: `#include "pddp_shim.cuh"`) makes the UNMODIFIED example
+// compile and link against libpddp.so, for any PLANT (oracle/Makefile target `example_shim` does exactly that, and
+// tests/test_gpu_shim.py runs the result):
+//   * mode G runs through the library: same positional arguments, x0 / u0 in and out (nisInitHelpers.cuh:745-746), Jout / alphaOut slots
+//     0..iters, the per-iteration timing arrays the example's statistics read, and the one-line summary of DDPWrappers.cuh:134 in the
+//     same format (max_d included).  The ~45 work pointers the reference threads through every call are owned by the library, so the
+//     shim hands back inert placeholders for them and keeps the solver handle in the slot of `d_x` (the first out-parameter).
+//   * modes C / CS (the reference's CPU twins) and S (SLQ) are declared so that the example compiles, and stop with a message when
+//     called: this library has no CPU path by design, and SLQ is out of scope (broken upstream, README.md:37).
 //
 // Compile-time macros of config.cuh are honoured as the front-end of the run-time pddp_config:
-//   NUM_TIME_STEPS, NUM_ALPHA, ALPHA_BASE, M_BLOCKS, MAX_ITER, TOL_COST, TOTAL_TIME, RHO_INIT, RHO_MIN, RHO_MAX,
-//   RHO_FACTOR, EXP_RED_MIN, EXP_RED_MAX, MAX_DEFECT_SIZE, _Q1, _Q2, _R, _QF1, _QF2, EE_COST with _Q_EE1 ... _QF_xEE   (PLANT must be 4;
-//   with EE_COST 1 the caller's 6-float goal pose is what xGoal holds, as in the reference).
+//   PLANT, NUM_TIME_STEPS, NUM_ALPHA, ALPHA_BASE, M_BLOCKS, MAX_ITER, TOL_COST, TOTAL_TIME, INTEGRATOR, RHO_INIT, RHO_MIN, RHO_MAX,
+//   RHO_FACTOR, EXP_RED_MIN, EXP_RED_MAX, MAX_DEFECT_SIZE; for the arm (PLANT 4) also _Q1, _Q2, _R, _QF1, _QF2 and EE_COST with
+//   _Q_EE1 ... _QF_xEE (with EE_COST 1 the caller's 6-float goal pose is what xGoal holds, as in the reference).  The other plants
+//   carry their cost weights in their plant files (plants/cost_{pend,cart,quad}.cuh), here: pddp_default_config.
 #pragma once
 #include "pddp.h"
 #include <cuda_runtime.h>
+// what config.cuh brings in for its includers (utils/cudaUtils.h:37-44, utils/threadUtils.h, utils/exampleUtils.cuh, <sys/time.h>)
+#include <sys/time.h>
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <iostream>
+#include <numeric>
+#include <string>
+#include <thread>
 #include <vector>
 
 #ifndef PLANT
 #define PLANT 4
-#endif
-#if PLANT != 4
-#error "pddp_shim.cuh: only PLANT 4 (Kuka iiwa14) is built"
 #endif
 #ifndef EE_COST
 #define EE_COST 0
@@ -44,20 +54,74 @@
 #define _QF_xEE 0.0
 #endif
 typedef float algType;
-#define NUM_POS 7
-#define STATE_SIZE 14
-#define CONTROL_SIZE 7
+// config.cuh:21-61
+#if PLANT == 1
+    #define NUM_POS 1
+    #define CONTROL_SIZE 1
+    #ifndef RHO_INIT
+    #define RHO_INIT 10.0
+    #endif
+#elif PLANT == 2
+    #define NUM_POS 2
+    #define CONTROL_SIZE 1
+    #ifndef MAX_DEFECT_SIZE
+    #define MAX_DEFECT_SIZE 0.75
+    #endif
+    #ifndef RHO_INIT
+    #define RHO_INIT 10.0
+    #endif
+#elif PLANT == 3
+    #define NUM_POS 6
+    #define CONTROL_SIZE 4
+    #ifndef ALPHA_BASE
+    #define ALPHA_BASE 0.5
+    #endif
+    #ifndef NUM_ALPHA
+    #define NUM_ALPHA 16
+    #endif
+    #ifndef RHO_INIT
+    #define RHO_INIT 1.0
+    #endif
+#elif PLANT == 4
+    #define NUM_POS 7
+    #define CONTROL_SIZE 7
+    #ifndef TOTAL_TIME
+    #define TOTAL_TIME 0.5
+    #endif
+    #ifndef NUM_TIME_STEPS
+    #define NUM_TIME_STEPS 64
+    #endif
+    #ifndef ALPHA_BASE
+    #define ALPHA_BASE 0.5
+    #endif
+    #ifndef NUM_ALPHA
+    #define NUM_ALPHA 16
+    #endif
+    #ifndef RHO_INIT
+    #define RHO_INIT 12.5
+    #endif
+    #ifndef INTEGRATOR
+    #define INTEGRATOR 1
+    #endif
+#else
+    #error "PLANT: 1 pendulum, 2 cart-pole, 3 quadrotor, 4 Kuka iiwa14"
+#endif
+#define STATE_SIZE (2*NUM_POS)
+// config.cuh:78-136
+#ifndef INTEGRATOR
+#define INTEGRATOR 3
+#endif
 #ifndef NUM_TIME_STEPS
-#define NUM_TIME_STEPS 64
+#define NUM_TIME_STEPS 128
 #endif
 #ifndef TOTAL_TIME
-#define TOTAL_TIME 0.5
+#define TOTAL_TIME 4.0
 #endif
 #ifndef NUM_ALPHA
-#define NUM_ALPHA 16
+#define NUM_ALPHA 32
 #endif
 #ifndef ALPHA_BASE
-#define ALPHA_BASE 0.5
+#define ALPHA_BASE 0.75
 #endif
 #ifndef M_BLOCKS
 #define M_BLOCKS 4
@@ -71,7 +135,7 @@ typedef float algType;
 #define TOL_COST 0.0001
 #endif
 #ifndef RHO_INIT
-#define RHO_INIT 12.5
+#define RHO_INIT 1.0
 #endif
 #ifndef RHO_MAX
 #define RHO_MAX 10000000.0
@@ -100,9 +164,10 @@ typedef float algType;
 #endif
 #define TIME_STEP (TOTAL_TIME/(NUM_TIME_STEPS-1))
 #define NUM_STREAMS 18
-#define PI 3.14159
 #define DIM_x_r STATE_SIZE
 #define DIM_u_r CONTROL_SIZE
+#define DIM_x_c 1
+#define DIM_u_c 1
 
 inline void pddp_shim_die(pddp_handle h, const char *what){
     // the reference's gpuAssert prints and exits (utils/cudaUtils.cu:31-37); the shim keeps that behaviour at this level only
@@ -116,11 +181,14 @@ void allocateMemory_GPU(T ***d_x, T ***h_d_x, T **d_xp, T **d_xp2, T ***d_u, T *
                         int *ld_x, int *ld_u, int *ld_P, int *ld_p, int *ld_AB, int *ld_H, int *ld_g, int *ld_KT, int *ld_du, int *ld_d, int *ld_A,
                         cudaStream_t **streams, T **d_I = nullptr, T **d_Tbody = nullptr){
     static_assert(sizeof(T) == sizeof(float), "the library computes in float (algType, config.cuh:74)");
-    pddp_config cfg; pddp_default_config_kuka(&cfg, NUM_TIME_STEPS, 1);
+    pddp_config cfg; if (pddp_default_config(&cfg, PLANT, NUM_TIME_STEPS, 1) != 0){ pddp_shim_die(nullptr, "pddp_default_config"); }
+    cfg.integrator = INTEGRATOR;
     cfg.n_alpha = NUM_ALPHA; cfg.alpha_base = (float)ALPHA_BASE; cfg.M = M_BLOCKS; cfg.max_iter = MAX_ITER; cfg.tol_cost = (float)TOL_COST;
     cfg.total_time = (float)TOTAL_TIME; cfg.rho_init = (float)RHO_INIT; cfg.rho_min = (float)RHO_MIN; cfg.rho_max = (float)RHO_MAX; cfg.rho_factor = (float)RHO_FACTOR;
     cfg.exp_red_min = (float)EXP_RED_MIN; cfg.exp_red_max = (float)EXP_RED_MAX; cfg.max_defect = (float)MAX_DEFECT_SIZE;
+#if PLANT == 4
     cfg.Q1 = (float)_Q1; cfg.Q2 = (float)_Q2; cfg.R = (float)_R; cfg.QF1 = (float)_QF1; cfg.QF2 = (float)_QF2;
+#endif
     cfg.ee_cost = EE_COST; cfg.Q_EE1 = (float)_Q_EE1; cfg.Q_EE2 = (float)_Q_EE2; cfg.QF_EE1 = (float)_QF_EE1; cfg.QF_EE2 = (float)_QF_EE2; cfg.R_EE = (float)_R_EE;
     cfg.Q_xdEE = (float)_Q_xdEE; cfg.QF_xdEE = (float)_QF_xdEE; cfg.Q_xEE = (float)_Q_xEE; cfg.QF_xEE = (float)_QF_xEE;
     pddp_handle h = nullptr;
@@ -154,11 +222,15 @@ void runiLQR_GPU(T *x0, T *u0, T *KT0, T *P0, T *p0, T *d0, T *xGoal, T *Jout, i
     // the reference only writes the slots it used (Jout[0..iters], alphaOut[0..iters])
     for (int i = 0; i <= iters; i++){ Jout[i] = Jtmp[i]; alphaOut[i] = atmp[i]; }
     *alphaIndex = atmp[iters] < 0 ? 0 : atmp[iters];
-    // whole-solve device times of each phase; the reference stores per-iteration host times, so the totals go to slot 0
-    *tTime = times[0]; simTime[0] = times[1]; sweepTime[0] = times[2]; bpTime[0] = times[3]; nisTime[0] = times[4]; *initTime = times[5];
-    for (int i = 1; i < iters; i++){ simTime[i] = sweepTime[i] = bpTime[i] = nisTime[i] = 0.0; }
+    // per-iteration times of each phase, as the reference's arrays hold them (device time here, host clock there): simTime / sweepTime /
+    // bpTime of iteration i in slot i-1, nisTime of the setup that follows it in the same slot (DDPWrappers.cuh:60-107)
+    *tTime = times[0]; *initTime = times[5];
+    const int cnt = pddp_last_iteration_times(h, simTime, sweepTime, bpTime, nisTime, MAX_ITER);
+    for (int i = cnt < 0 ? 0 : cnt; i < MAX_ITER; i++){ simTime[i] = sweepTime[i] = bpTime[i] = nisTime[i] = 0.0; }
+    float max_d = 0.f; if (pddp_final_max_defect(h, &max_d) != 0){ pddp_shim_die(h, "pddp_final_max_defect"); }
+    if (d){ d[*alphaIndex] = max_d; }
     std::printf("GPU Parallel blocks:[%d] t:[%f] with FP[%f], FS[%f], BP[%f], NIU[%f] Xf:[%.4f, %.4f] iters:[%d] cost:[%f] max_d[%f]\n",
-                M_BLOCKS_B, *tTime, *simTime, *sweepTime, *bpTime, *nisTime, x0[ld_x*(NUM_TIME_STEPS-1)], x0[ld_x*(NUM_TIME_STEPS-1)+1], iters, (double)Jtmp[iters], 0.0);
+                M_BLOCKS_B, *tTime, *simTime, *sweepTime, *bpTime, *nisTime, x0[ld_x*(NUM_TIME_STEPS-1)], x0[ld_x*(NUM_TIME_STEPS-1)+1], iters, (double)Jtmp[iters], (double)max_d);
 }
 
 template <typename T>
@@ -169,3 +241,16 @@ void freeMemory_GPU(T **d_x, T **h_d_x, T *d_xp, T *d_xp2, T **d_u, T **h_d_u, T
     pddp_destroy(reinterpret_cast<pddp_handle>(d_x));
     std::free(xGoal); std::free(d); std::free(J); std::free(dJexp); std::free(alpha); std::free(alphaIndex); std::free(err);
 }
+
+// ---- the reference's CPU twins and SLQ: declared so that the example compiles; calling them stops the program ------------------------
+inline void pddp_shim_not_built(const char *what){
+    std::fprintf(stderr, "%s: not built -- libpddp has no CPU path (by design: no CPU fallback) and no SLQ variant; run the example in mode G\n", what);
+    std::exit(2);
+}
+template <typename T, typename... A> void allocateMemory_CPU(A...){ pddp_shim_not_built("allocateMemory_CPU"); }
+template <typename T, typename... A> void allocateMemory_CPU2(A...){ pddp_shim_not_built("allocateMemory_CPU2"); }
+template <typename T, typename... A> void runiLQR_CPU(A...){ pddp_shim_not_built("runiLQR_CPU"); }
+template <typename T, typename... A> void runiLQR_CPU2(A...){ pddp_shim_not_built("runiLQR_CPU2"); }
+template <typename T, typename... A> void freeMemory_CPU(A...){ pddp_shim_not_built("freeMemory_CPU"); }
+template <typename T, typename... A> void freeMemory_CPU2(A...){ pddp_shim_not_built("freeMemory_CPU2"); }
+template <typename T, typename... A> void runSLQ_GPU(A...){ pddp_shim_not_built("runSLQ_GPU"); }

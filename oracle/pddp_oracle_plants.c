@@ -167,11 +167,48 @@ static void quad_gradient(const float *x, const float *u, float *qdd, float *dqd
     #undef D_
 }
 
+/* ------------------------------------------------------------------ GPU arithmetic of the three plants
+ * Which multiply-adds the device build fuses inside these expressions follows no rule that could be restated by hand (nvcc fuses the
+ * RIGHT product of s3*s5 + c3*c5*s4, the left one elsewhere; ptxas fuses some of what NVVM left) and a C compiler's own contraction
+ * differs from it, so the ORACLE_FMA build takes the statements read off nvcc's PTX for the same closed forms (oracle/tools/ptx2c.py).
+ * Both variants are pinned: the expressions above to the reference's host build, these to its GPU run. */
+#if ORACLE_FMA && !defined(ORACLE_F64)
+#include <stdint.h>
+static float bitsf(uint32_t v){ float f; memcpy(&f, &v, 4); return f; }
+static double bitsd(uint64_t v){ double f; memcpy(&f, &v, 8); return f; }
+#define SIN64(x) sin(x)
+#include "plants_gpu_arith.inc"
+#define PLANT_DYN(nm, x, u, qdd) nm##_dynamics_gpu(x, u, qdd)
+/* gradient = the acceleration (when asked for) + the block of the real kernel that fills s_dqdd, fed with the sines / cosines it
+ * receives from the inlined library code ahead of it.  Live-in order of each block: see plants_gpu_arith.inc; which trigonometric
+ * value sits in which register was resolved against the reference's GPU dumps (tools/quad_livein_search.py). */
+int orc_quad_perm[6] = {0, 2, 4, 3, 5, 1};
+static void pend_gradient_gpu(const float *x, const float *u, float *qdd, float *dqdd){
+    if (qdd){ pend_dynamics_gpu(x, u, qdd); }
+    dqdd[0] = PEND_G*COSF(x[0]); dqdd[1] = 0.0; dqdd[2] = 1;          /* one double product: nothing to fuse */
+}
+static void cart_gradient_gpu(const float *x, const float *u, float *qdd, float *dqdd){
+    if (qdd){ cart_dynamics_gpu(x, u, qdd); }
+    float li[2] = {COSF(x[1]), SINF(x[1])}; cart_gradient_tail_gpu(x, u, li, dqdd);
+}
+static void quad_gradient_gpu(const float *x, const float *u, float *qdd, float *dqdd){
+    if (qdd){ quad_dynamics_gpu(x, u, qdd); }
+    const float t[6] = {COSF(x[3]), COSF(x[4]), COSF(x[5]), SINF(x[3]), SINF(x[4]), SINF(x[5])};
+    float li[6]; for (int i = 0; i < 6; i++){ li[i] = t[orc_quad_perm[i]]; }
+    memset(dqdd, 0, sizeof(float)*6*16);
+    quad_gradient_tail_gpu(x, u, li, dqdd);
+}
+#define PLANT_GRAD(nm, x, u, qdd, dqdd) nm##_gradient_gpu(x, u, qdd, dqdd)
+#else
+#define PLANT_DYN(nm, x, u, qdd) nm##_dynamics(x, u, qdd)
+#define PLANT_GRAD(nm, x, u, qdd, dqdd) nm##_gradient(x, u, qdd, dqdd)
+#endif
+
 void orc_plant_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd){
-    if (c->plant == ORC_PLANT_PEND){ pend_dynamics(x, u, qdd); } else if (c->plant == ORC_PLANT_CART){ cart_dynamics(x, u, qdd); } else { quad_dynamics(x, u, qdd); }
+    if (c->plant == ORC_PLANT_PEND){ PLANT_DYN(pend, x, u, qdd); } else if (c->plant == ORC_PLANT_CART){ PLANT_DYN(cart, x, u, qdd); } else { PLANT_DYN(quad, x, u, qdd); }
 }
 void orc_plant_gradient(const orc_cfg *c, const float *x, const float *u, float *qdd, float *dqdd){
-    if (c->plant == ORC_PLANT_PEND){ pend_gradient(x, u, qdd, dqdd); } else if (c->plant == ORC_PLANT_CART){ cart_gradient(x, u, qdd, dqdd); } else { quad_gradient(x, u, qdd, dqdd); }
+    if (c->plant == ORC_PLANT_PEND){ PLANT_GRAD(pend, x, u, qdd, dqdd); } else if (c->plant == ORC_PLANT_CART){ PLANT_GRAD(cart, x, u, qdd, dqdd); } else { PLANT_GRAD(quad, x, u, qdd, dqdd); }
 }
 
 /* ------------------------------------------------------------------ costs: cost_pend.cuh:20-54, cost_cart.cuh:19-68, cost_quad.cuh:19-55
@@ -203,66 +240,86 @@ void orc_dynamics(const orc_cfg *c, const float *x, const float *u, float *qdd);
 void orc_dynamics_gradient_any(const orc_cfg *c, const float *x, const float *u, float *qdd, float *dqdd);
 static float dxd(const float *dqdd, int np, int r, int c){ return r < np ? (float)(r + np == c ? 1 : 0) : dqdd[(c-1)*np + r]; }   /* :15-17 */
 
+/* The integrators are float arithmetic throughout, and here the device build's contraction is regular (read off the PTX of
+ * plugin/integrators.cuh and of the reference's GPU dumps): a product feeding a sum is fused, of two products the left one. */
+#if ORACLE_FMA && !defined(ORACLE_F64)
+#define FMAF(a,b,c) fmaf((a),(b),(c))
+#else
+#define FMAF(a,b,c) ((float)((float)((a)*(b)) + (c)))
+#endif
+#define MULF(a,b) ((float)((a)*(b)))
+#define ADDF(a,b) ((float)((a)+(b)))
+#define SUBF(a,b) ((float)((a)-(b)))
+
 void orc_integrator_generic(const orc_cfg *c, const float *x, const float *u, float *xn){
-    const int np = c->npos; const float dt = c->dt;
+    const int np = c->npos; const float dt = c->dt, h = MULF((float)(0.5), dt);
     float a1[ORC_MAX_N], a2[ORC_MAX_N], a3[ORC_MAX_N], x2[ORC_MAX_N], x3[ORC_MAX_N];
     orc_dynamics(c, x, u, a1);
     if (c->integrator == ORC_INT_EULER){                                     /* :24-36 */
-        for (int i = 0; i < np; i++){ xn[i] = x[i] + dt*x[i+np]; xn[i+np] = x[i+np] + dt*a1[i]; }
+        for (int i = 0; i < np; i++){ xn[i] = FMAF(dt, x[i+np], x[i]); xn[i+np] = FMAF(dt, a1[i], x[i+np]); }
     } else if (c->integrator == ORC_INT_MIDPOINT){                           /* :56-83: q advances with the INITIAL velocity (:78) */
-        for (int i = 0; i < np; i++){ x2[i] = x[i] + (float)(0.5)*dt*x[i+np]; x2[i+np] = x[i+np] + (float)(0.5)*dt*a1[i]; }
+        for (int i = 0; i < np; i++){ x2[i] = FMAF(h, x[i+np], x[i]); x2[i+np] = FMAF(h, a1[i], x[i+np]); }
         orc_dynamics(c, x2, u, a2);
-        for (int i = 0; i < np; i++){ xn[i] = x[i] + dt*x[i+np]; xn[i+np] = x[i+np] + dt*a2[i]; }
+        for (int i = 0; i < np; i++){ xn[i] = FMAF(dt, x[i+np], x[i]); xn[i+np] = FMAF(dt, a2[i], x[i+np]); }
     } else {                                                                  /* RK3 :123-160 */
-        for (int i = 0; i < np; i++){ x2[i] = x[i] + (float)(0.5)*dt*x[i+np]; x2[i+np] = x[i+np] + (float)(0.5)*dt*a1[i]; }
+        const float dt6 = (float)(dt/(float)(6));
+        for (int i = 0; i < np; i++){ x2[i] = FMAF(h, x[i+np], x[i]); x2[i+np] = FMAF(h, a1[i], x[i+np]); }
         orc_dynamics(c, x2, u, a2);
-        for (int i = 0; i < np; i++){ x3[i] = x[i] + dt*((float)(2)*x2[i+np] - x[i+np]); x3[i+np] = x[i+np] + dt*((float)(2)*a2[i] - a1[i]); }
+        for (int i = 0; i < np; i++){      /* 2*v is exact, so 2*v - w is one rounding with or without fusion */
+            x3[i] = FMAF(dt, SUBF(MULF((float)(2), x2[i+np]), x[i+np]), x[i]); x3[i+np] = FMAF(dt, SUBF(MULF((float)(2), a2[i]), a1[i]), x[i+np]);
+        }
         orc_dynamics(c, x3, u, a3);
         for (int i = 0; i < np; i++){
-            xn[i] = x[i] + (dt/(float)(6))*(x[i+np] + (float)(4)*x2[i+np] + x3[i+np]);
-            xn[i+np] = x[i+np] + (dt/(float)(6))*(a1[i] + (float)(4)*a2[i] + a3[i]);
+            xn[i] = FMAF(dt6, ADDF(FMAF((float)(4), x2[i+np], x[i+np]), x3[i+np]), x[i]);
+            xn[i+np] = FMAF(dt6, ADDF(FMAF((float)(4), a2[i], a1[i]), a3[i]), x[i+np]);
         }
     }
 }
 
 #define ORC_ND (ORC_MAX_N*(ORC_MAX_N + ORC_MAX_M))
 void orc_integrator_gradient_generic(const orc_cfg *c, const float *x, const float *u, float *AB, float *qdd_out){
-    const int np = c->npos, n = c->n, nm = c->n + c->m; const float dt = c->dt;
+    const int np = c->npos, n = c->n, nm = c->n + c->m; const float dt = c->dt, h = MULF((float)(0.5), dt), dt2 = MULF((float)(2), dt);
     float a1[ORC_MAX_N], a2[ORC_MAX_N], a3[ORC_MAX_N], x2[ORC_MAX_N], x3[ORC_MAX_N];
     float d1[ORC_ND], d2[ORC_ND], d3[ORC_ND], G1[ORC_ND], G2[ORC_ND];
     orc_dynamics_gradient_any(c, x, u, a1, d1);
     if (qdd_out){ for (int i = 0; i < np; i++){ qdd_out[i] = a1[i]; } }
+    #define DLT(a, b) ((float)((a) == (b) ? 1 : 0))
     if (c->integrator == ORC_INT_EULER){                                     /* :38-53 */
-        for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){ AB[ky*n + kx] = (float)(ky == kx ? 1 : 0) + dt*dxd(d1, np, kx, ky); } }
+        for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){ AB[ky*n + kx] = FMAF(dt, dxd(d1, np, kx, ky), DLT(ky, kx)); } }
     } else if (c->integrator == ORC_INT_MIDPOINT){                           /* :86-121 */
-        for (int i = 0; i < np; i++){ x2[i] = x[i] + (float)(0.5)*dt*x[i+np]; x2[i+np] = x[i+np] + (float)(0.5)*dt*a1[i]; }
+        for (int i = 0; i < np; i++){ x2[i] = FMAF(h, x[i+np], x[i]); x2[i+np] = FMAF(h, a1[i], x[i+np]); }
         orc_dynamics_gradient_any(c, x2, u, a2, d2);
         for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){
             float val = 0;
             for (int i = 0; i < n; i++){
-                float A2_val = (float)(kx == i ? 1 : 0) + (float)(0.5)*dt*dxd(d2, np, kx, i);
-                float AB1_val = (float)(ky == i ? 1 : 0) + (float)(0.5)*dt*dxd(d1, np, i, ky);
-                val += A2_val * AB1_val;
+                const float A2_val = FMAF(h, dxd(d2, np, kx, i), DLT(kx, i)), AB1_val = FMAF(h, dxd(d1, np, i, ky), DLT(ky, i));
+                val = FMAF(A2_val, AB1_val, val);
             }
-            AB[ky*n + kx] = val + (ky < n ? (float)(0) : (float)(0.5)*dt*dxd(d2, np, kx, ky));
+            /* the B-column term is formed in its own branch of the kernel and added behind it: a rounded product, then a sum */
+            AB[ky*n + kx] = ADDF(val, (ky < n ? (float)(0) : MULF(h, dxd(d2, np, kx, ky))));
         }}
     } else {                                                                  /* RK3 :162-233, stage states as written (:181-182,190-191) */
-        for (int i = 0; i < np; i++){ x2[i] = x[i] + (float)(0.5)*dt*x[i+np]; x2[i+np] = x[i] + (float)(0.5)*dt*a1[i]; }
+        const float dt6 = (float)(dt/(float)(6)), dt23 = (float)(dt2/(float)(3));
+        for (int i = 0; i < np; i++){ x2[i] = FMAF(h, x[i+np], x[i]); x2[i+np] = FMAF(h, a1[i], x[i]); }
         orc_dynamics_gradient_any(c, x2, u, a2, d2);
-        for (int i = 0; i < np; i++){ x3[i] = x[i] + dt*x[i+np] + (float)(2)*dt*x2[i+np]; x3[i+np] = x[i] + dt*a1[i] + (float)(2)*dt*a2[i]; }
+        for (int i = 0; i < np; i++){ x3[i] = FMAF(dt2, x2[i+np], FMAF(dt, x[i+np], x[i])); x3[i+np] = FMAF(dt2, a2[i], FMAF(dt, a1[i], x[i])); }
         orc_dynamics_gradient_any(c, x3, u, a3, d3);
         for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){
             float val = 0;
-            for (int i = 0; i < n; i++){ val += dxd(d2, np, kx, i)*((float)(0.5)*dt*dxd(d1, np, i, ky) + (float)(ky == i ? 1 : 0)); }
-            G1[kx + n*ky] = val + (ky < n ? (float)(0) : dxd(d2, np, kx, ky));
+            for (int i = 0; i < n; i++){ val = FMAF(dxd(d2, np, kx, i), FMAF(h, dxd(d1, np, i, ky), DLT(ky, i)), val); }
+            G1[kx + n*ky] = ADDF(val, (ky < n ? (float)(0) : dxd(d2, np, kx, ky)));
         }}
         for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){
             float val = 0;
-            for (int i = 0; i < n; i++){ val += dxd(d3, np, kx, i)*((float)(2)*dt*G1[ky*n + i] - dt*dxd(d1, np, i, ky) + (float)(ky == i ? 1 : 0)); }
-            G2[kx + n*ky] = val + (ky < n ? (float)(0) : dxd(d3, np, kx, ky));
+            for (int i = 0; i < n; i++){
+                const float inner = ADDF(FMAF(dt2, G1[ky*n + i], -MULF(dt, dxd(d1, np, i, ky))), DLT(ky, i));
+                val = FMAF(dxd(d3, np, kx, i), inner, val);
+            }
+            G2[kx + n*ky] = ADDF(val, (ky < n ? (float)(0) : dxd(d3, np, kx, ky)));
         }}
         for (int ky = 0; ky < nm; ky++){ for (int kx = 0; kx < n; kx++){
-            AB[kx + n*ky] = (dt/(float)(6))*dxd(d1, np, kx, ky) + ((float)(2)*dt/(float)(3))*G1[kx + n*ky] + (dt/(float)(6))*G2[kx + n*ky] + (float)(kx == ky ? 1 : 0);
+            AB[kx + n*ky] = ADDF(FMAF(dt6, G2[kx + n*ky], FMAF(dt6, dxd(d1, np, kx, ky), MULF(dt23, G1[kx + n*ky]))), DLT(kx, ky));
         }}
     }
+    #undef DLT
 }

@@ -46,7 +46,7 @@ EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
            "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
            "pddp_default_config", "pddp_plant_dims", "pddp_register_plant", "pddp_load_plant_library", "pddp_plant_error", "pddp_make_inputs",
-           "pddp_unit_integrator", "pddp_unit_cost",
+           "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -100,6 +100,8 @@ def load_library():
     L.pddp_load_plant_library.argtypes = [C.c_char_p]
     L.pddp_plant_error.argtypes = []; L.pddp_plant_error.restype = C.c_char_p
     L.pddp_make_inputs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, FP, FP, FP]
+    L.pddp_last_iteration_times.argtypes = [H, DP, DP, DP, DP, C.c_int]
+    L.pddp_final_max_defect.argtypes = [H, FP]
     L.pddp_unit_integrator.argtypes = [H, FP, FP, C.c_int, FP]
     L.pddp_unit_cost.argtypes = [H, FP, FP, FP, IP, C.c_int, FP, FP, FP]
     _lib = L
@@ -299,6 +301,17 @@ class Solver:
     def set_groups(self, groups):
         """Problem groups iterated on separate streams (overlap of latency- and throughput-bound kernels); returns the value in effect."""
         return int(self.L.pddp_set_groups(self.h, groups))
+
+    def iteration_times(self):
+        """per-iteration device times (ms) of the last timed solve run as one problem group: dict(sim, sweep, bp, nis) of arrays"""
+        cap = self.cfg.max_iter; a = [np.zeros(cap, np.float64) for _ in range(4)]
+        cnt = self.L.pddp_last_iteration_times(self.h, *[v.ctypes.data_as(DP) for v in a], cap)
+        return dict(zip(("sim", "sweep", "bp", "nis"), [v[:cnt] for v in a]))
+
+    def final_max_defect(self):
+        d = np.zeros(self.cfg.batch, np.float32)
+        self._ck(self.L.pddp_final_max_defect(self.h, d.ctypes.data_as(FP)), "pddp_final_max_defect")
+        return d
 
     def launch_count(self):
         return int(self.L.pddp_last_launch_count(self.h))

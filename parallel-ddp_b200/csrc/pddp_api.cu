@@ -43,6 +43,7 @@ struct pddp_solver {
     int *h_nactive = nullptr;
     cudaEvent_t ev[8];
     double last_ms = 0; int last_launches = 0;
+    std::vector<double> it_ms[4];                                              // per-iteration device times of the last timed solve: sim(+selection), sweep, bp, nis
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
     float *d_xTarget = nullptr;
     int *d_cost_shift = nullptr; bool use_cost_shift = false;
@@ -368,7 +369,8 @@ static int launch_nis(pddp_handle h, cudaStream_t st, int b0, int nb){
 static int run_iterations(pddp_handle h, double *times_ms, int groups){
     DevState &S = h->S;
     const bool timing = times_ms != nullptr && groups == 1;
-    std::vector<cudaEvent_t> evs;
+    struct EventBag { std::vector<cudaEvent_t> v; ~EventBag(){ for (auto e : v){ cudaEventDestroy(e); } } } bag;     // released on every path out
+    std::vector<cudaEvent_t> &evs = bag.v;
     auto mark = [&](){ if (timing){ cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); } };
     const bool poll = h->cfg.tol_cost > 0.0f;
     // fork: every group stream starts after the setup on stream 0
@@ -399,8 +401,12 @@ static int run_iterations(pddp_handle h, double *times_ms, int groups){
     if (timing){
         CK(cudaStreamSynchronize(h->stream));
         double acc[5] = {0,0,0,0,0};
-        for (int it = 0; it < it_done; it++){ for (int ph = 0; ph < 5; ph++){ float ms = 0; cudaEventElapsedTime(&ms, evs[it*5+ph], evs[it*5+ph+1]); acc[ph] += ms; } }
-        for (auto e : evs){ cudaEventDestroy(e); }
+        for (auto &v : h->it_ms){ v.assign(it_done, 0.0); }
+        for (int it = 0; it < it_done; it++){
+            float ph_ms[5];
+            for (int ph = 0; ph < 5; ph++){ ph_ms[ph] = 0; cudaEventElapsedTime(&ph_ms[ph], evs[it*5+ph], evs[it*5+ph+1]); acc[ph] += ph_ms[ph]; }
+            h->it_ms[0][it] = ph_ms[2] + ph_ms[3]; h->it_ms[1][it] = ph_ms[1]; h->it_ms[2][it] = ph_ms[0]; h->it_ms[3][it] = ph_ms[4];
+        }
         // reference order of the timing outputs: tTime, simTime, sweepTime, bpTime, nisTime, initTime (DDPWrappers.cuh:11)
         times_ms[1] = acc[2] + acc[3]; times_ms[2] = acc[1]; times_ms[3] = acc[0]; times_ms[4] = acc[4];
     }
@@ -733,6 +739,33 @@ extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
     return e == cudaSuccess ? 0 : PDDP_E_CUDA;
 }
 extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
+// per-iteration device times (ms) of the last solve that was given a times_ms array and ran as one problem group: what the reference
+// stores in its simTime / sweepTime / bpTime / nisTime arrays (DDPWrappers.cuh:60-107; there: host clock around each phase)
+extern "C" int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, double *bp_ms, double *nis_ms, int capacity){
+    if (!h || capacity < 0){ return PDDP_E_INVALID; }
+    const int cnt = (int)h->it_ms[0].size() < capacity ? (int)h->it_ms[0].size() : capacity;
+    for (int i = 0; i < cnt; i++){
+        if (sim_ms){ sim_ms[i] = h->it_ms[0][i]; } if (sweep_ms){ sweep_ms[i] = h->it_ms[1][i]; } if (bp_ms){ bp_ms[i] = h->it_ms[2][i]; } if (nis_ms){ nis_ms[i] = h->it_ms[3][i]; }
+    }
+    return cnt;
+}
+// largest L1 defect on the shooting-interval boundaries of every problem's final trajectory: what storeVarsGPU computes for the summary
+// line of runiLQR_GPU (nisInitHelpers.cuh:739-750, DDPWrappers.cuh:134 `max_d`)
+extern "C" int pddp_final_max_defect(pddp_handle h, float *max_d){
+    if (!h || !max_d){ return PDDP_E_INVALID; }
+    DevState &S = h->S; const size_t B = S.B, N = S.N, n = S.n, A = S.A; const int NBF = S.N / S.M;
+    CK(cudaSetDevice(h->cfg.device)); for (auto st : h->gstreams){ CK(cudaStreamSynchronize(st)); }
+    std::vector<int> src(B); std::vector<float> dT(B*A), dp(B*N*n);
+    CK(cudaMemcpy(src.data(), S.final_src, B*sizeof(int), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(dT.data(), S.dT, B*A*4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dp.data(), S.dp, B*N*n*4, cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < B; b++){
+        if (src[b] >= 0){ max_d[b] = dT[b*A + src[b]]; continue; }
+        float best = 0.f;                                   // the accepted trajectory of an earlier iteration: defectKern's sum and maximum (fpHelpers.cuh:94-111)
+        for (int k = NBF - 1; k < (int)N - 1; k += NBF){ volatile float acc = 0.f; for (size_t c = 0; c < n; c++){ acc = acc + std::fabs(dp[(b*N + k)*n + c]); } best = acc > best ? (float)acc : best; }
+        max_d[b] = best;
+    }
+    return 0;
+}
 extern "C" int pddp_set_groups(pddp_handle h, int groups){
     if (!h || groups < 1 || groups > 8){ return PDDP_E_INVALID; }
     h->groups = (h->S.B >= 2*groups || groups == 1) ? groups : 1; return h->groups;

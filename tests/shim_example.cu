@@ -7,6 +7,9 @@
 #define NUM_TIME_STEPS 32
 #define MAX_ITER 5
 #include "../include/pddp_shim.cuh"
+#ifndef PI
+#define PI 3.14159        // the example defines it itself (WAFR_iLQR_examples.cu:36)
+#endif
 int main(){
     typedef algType T;
     int ld_x, ld_u, ld_P, ld_p, ld_AB, ld_H, ld_g, ld_KT, ld_du, ld_d, ld_A; cudaStream_t *streams; T *alpha, *d_alpha; int *alphaIndex;

@@ -168,16 +168,19 @@ def test_quadrotor_receding_horizon_vs_oracle():
         L.orc_mpc_free(q)
 
 
-# ---------------------------------------------------------------------------------------------------------------- oracle pins (GPU arithmetic)
-@pytest.mark.parametrize("tag", SOLVE_TAGS)
-def test_oracle_fma_vs_reference_gpu_solves(tag):
-    """liboracle_fma.so against the reference's GPU run: whole 100-iteration solves (needs no device, but its fixtures come from one)"""
-    plant, integ, N, A = ol.parse_plant_tag(tag)
-    g = golden(tag + "_solve_G_s0-3")
-    _, ocfg = _cfgs(tag)
-    x0, u0, xg = pddp.make_inputs(plant, N, 4, seed0=0)
-    L1 = ocfg.max_iter + 1
-    for b in range(4 if N < 256 else 1):
-        it, ox, ou, oJ, oa = _oracle_solve(ocfg, x0[b], u0[b], xg[b])
-        assert _same(oa, g["alphaOut"].reshape(4, L1)[b]) and _same(oJ, g["Jout"].reshape(4, L1)[b]), (tag, b)
-        assert _same(ox, g["x_out"].reshape(4, N, ocfg.n)[b]) and _same(ou, g["u_out"].reshape(4, N, ocfg.m)[b]), (tag, b)
+# ---------------------------------------------------------------------------------------------------------------- phase by phase
+TRACES_G = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(ROOT, "tests", "golden", "p?_i?_N*_trace_G_s*.npz")))
+
+
+@pytest.mark.parametrize("name", TRACES_G)
+def test_phases_vs_reference_gpu_trace(name):
+    """every array the reference's GPU run dumped in its first iterations (P, p, KT, du, A-BK, Bdu, expected reduction, swept and simulated
+    x, u, d of every step size, J, defects, AB, H, g, rho schedule), phase by phase through the phase-level entry points"""
+    from test_gpu_parity import _phase_walk
+    tag = name.split("_trace_")[0]; plant, integ, N, A = ol.parse_plant_tag(tag)
+    tol = 0.0001 if name.endswith("_s2") else 0.0
+    c, _ = _cfgs(tag, batch=1, tol_cost=tol)
+    res = _phase_walk(golden(name), tol, s=pddp.Solver(c))
+    bad = [k for k, v in res.items() if not v[0]]
+    report(test="plant_phases_vs_refG", golden=name, nchecks=len(res), inexact=bad[:20])
+    assert not bad, bad[:10]

@@ -130,3 +130,56 @@ def test_plugin_plant_headers_vs_reference_host(tag, plant_host_libs):
         L.ph_integrator(integ, ol.fptr(x[k]), ol.fptr(u[k]), dt, ol.fptr(xn))
         ol.lib(False).orc_integrator(C.byref(cfg), ol.fptr(x[k]), ol.fptr(u[k]), ol.fptr(xo))
         assert np.array_equal(xn, xo), (tag, k)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arithmetic
+# liboracle_fma.so against the reference's GPU run of these plants on a B200 (tests/golden/p*_{unit,trace,solve}_G*.npz; generated by
+# tests/golden/make_goldens.py gpu on the GPU box, imported here): needs no device.
+SOLVES_G = ["p1_i3_N32_a1", "p1_i2_N32_a4", "p2_i3_N64_a8", "p2_i1_N32_a8", "p3_i3_N64_a16", "p3_i2_N32_a16", "p3_i3_N256_a32"]
+TRACES_G = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "p?_i?_N*_trace_G_s*.npz")))
+
+
+@pytest.mark.parametrize("tag", UNIT_TAGS)
+def test_oracle_gpu_arithmetic_plant_functions_vs_reference_gpu(tag):
+    plant, integ, N, A = ol.parse_plant_tag(tag)
+    g = _gold(tag + "_unit_G")
+    L = ol.lib(True); cfg = ol.plant_cfg(plant, N, A, integ, fma=True); cp = C.byref(cfg)
+    n, m, npos = cfg.n, cfg.m, cfg.npos; nm = n + m; ns = int(g["meta"][3])
+    x = g["x"].reshape(ns, n); u = g["u"].reshape(ns, m)
+    for k in range(ns):
+        q = np.zeros(npos, np.float32); L.orc_dynamics(cp, ol.fptr(x[k]), ol.fptr(u[k]), ol.fptr(q))
+        assert np.array_equal(q, g["qdd"].reshape(ns, npos)[k]), (tag, k)
+        AB = np.zeros(n*nm, np.float32); q2 = np.zeros(npos, np.float32)
+        L.orc_integrator_gradient(cp, ol.fptr(x[k]), ol.fptr(u[k]), ol.fptr(AB), ol.fptr(q2))
+        assert np.array_equal(AB, g["AB"].reshape(ns, -1)[k]), (tag, k)
+        assert np.array_equal(q2, g["qdd_from_grad"].reshape(ns, npos)[k]), (tag, k)
+
+
+@pytest.mark.parametrize("name", TRACES_G)
+def test_oracle_gpu_arithmetic_whole_solve_phases_vs_reference_gpu(name):
+    tag = name.split("_trace_")[0]; plant, integ, N, A = ol.parse_plant_tag(tag)
+    tr = _gold(name)
+    tol = 0.0001 if name.endswith("_s2") else 0.0
+    cfg = ol.plant_cfg(plant, N, A, integ, fma=True, tol_cost=tol, host_expred=False)
+    res, aOut, Jout = trace_check.run_trace_compare(tr, fma=True, host_expred=False, tol_cost=tol, cfg=cfg, trig_limit=1.0e5)
+    bad = {k: v for k, v in res.items() if not v[0]}
+    assert not bad, (name, list(bad.items())[:8])
+
+
+@pytest.mark.parametrize("tag", SOLVES_G)
+def test_oracle_gpu_arithmetic_solves_vs_reference_gpu(tag):
+    """100-iteration solves of the reference's GPU build, seeds 0-3: cost trace, step sizes, final trajectories"""
+    import importlib
+    pddp = importlib.import_module("parallel-ddp_b200")
+    plant, integ, N, A = ol.parse_plant_tag(tag)
+    g = _gold(tag + "_solve_G_s0-3")
+    cfg = ol.plant_cfg(plant, N, A, integ, fma=True); L = ol.lib(True)
+    x0, u0, xg = pddp.make_inputs(plant, N, 4, seed0=0)
+    L1 = cfg.max_iter + 1; n, m = cfg.n, cfg.m
+    for b in ((1, 2, 3) if N < 256 else (2,)):          # seed 0 draws the same numbers as seed 1 (minstd_rand0 maps 0 to 1)
+        ox = np.zeros((N, n), np.float32); ou = np.zeros((N, m), np.float32)
+        oJ = np.full(L1, np.nan, np.float32); oa = np.full(L1, -99, np.int32)
+        L.orc_solve(C.byref(cfg), ol.fptr(x0[b]), ol.fptr(u0[b]), ol.fptr(xg[b]), ol.fptr(ox), ol.fptr(ou), ol.fptr(oJ), ol.iptr(oa))
+        assert np.array_equal(oa, g["alphaOut"].reshape(4, L1)[b]), (tag, b, oa[:12], g["alphaOut"].reshape(4, L1)[b][:12])
+        assert np.array_equal(oJ, g["Jout"].reshape(4, L1)[b], equal_nan=True), (tag, b)
+        assert np.array_equal(ox, g["x_out"].reshape(4, N, n)[b]) and np.array_equal(ou, g["u_out"].reshape(4, N, m)[b]), (tag, b)
