@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 N_KNOTS, N_ALPHA, M_BLOCKS, BATCH_PER_GPU, MAX_ITER = 128, 16, 4, int(os.environ.get("PDDP_BENCH_BATCH", "64")), 100   # 64 = the headline; the env is for the strong-scaling data point (512 on one GPU)
 BP_BYTES_PER_PROBLEM = 4 * ((N_KNOTS - 1) * 1281 + 4 * 238 + 3 * 14 + 2 * 210 + 3 * 4)   # = 656452
+STRONG_BATCH = 512          # BASELINE configs[3]
 METRIC = "ilqr_iterations_per_sec"
 UNIT = "iterations/s"
 CONFIG = {"workload": f"configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batch={BATCH_PER_GPU} per GPU, TOL_COST=0 (100 iterations per problem)",
@@ -44,6 +45,14 @@ CONFIG = {"workload": f"configs[2]: Kuka iiwa14 N=128 knots, alpha=16, M=4, batc
 BENCH_EE = bool(int(os.environ.get("PDDP_BENCH_EE", "0") or 0))
 if BENCH_EE:
     CONFIG["workload"] += " -- end-effector cost (EE_COST 1)"; CONFIG["cost"] = "end_effector"
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("kernels.cuh", "dev_state.cuh", "pddp_math.cuh"):
+        h.update(open(os.path.join(ROOT, "parallel-ddp_b200", "csrc", f), "rb").read())
+    return h.hexdigest()
 
 
 def peaks():
@@ -114,6 +123,24 @@ def oracle_port_run(nprob):
     return tot / dt, tot, dt, 1
 
 
+def ref_gpu_run(nseeds=8):
+    """The UNMODIFIED reference's own GPU build (runiLQR_GPU, compiled for sm_100 by oracle/Makefile) on the first `nseeds` benchmark
+    problems, one after the other as the reference solves them: north_star's ">= 10x the reference GPU build" denominator."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_driver_N{N_KNOTS}")
+    if not os.path.exists(exe):
+        return None
+    best = None
+    for _ in range(2):                                   # the first call pays context creation inside its first solve
+        r = subprocess.run([exe, "time", "G", "0", str(nseeds), "0.0"], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        m = re.search(r"REFSUMMARY (\{.*\})", r.stderr)
+        if not m:
+            return None
+        d = json.loads(m.group(1)); v = d["total_iters"] / (d["sum_solve_ms"] / 1000.0)
+        best = max(best or 0.0, v)
+    return {"value": best, "unit": UNIT, "kind": "reference GPU build (oracle/_ref/ref_driver_N128, mode G, unmodified reference kernels on this GPU)",
+            "sample": f"{nseeds} benchmark problems (seeds 0..{nseeds-1}) x 100 iterations, solved one after the other (the reference has no batch), best of 2 runs"}
+
+
 def cpu_baseline(nseeds=16):      # about 11 s of host work on the GPU box (16 threads)
     r = ref_cpu_run(nseeds)
     if r:
@@ -163,9 +190,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout carries exactly one JSON line here
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("PDDP_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left as the caller set it (the driver reads the rank count from NCCL's INFO lines).  NCCL writes those to STDOUT
+        # unless told otherwise, and stdout carries exactly one JSON line here: without a NCCL_DEBUG_FILE they go to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pddp = importlib.import_module("parallel-ddp_b200")
     B, N, L1 = BATCH_PER_GPU, N_KNOTS, MAX_ITER + 1
@@ -205,7 +233,7 @@ def main():
         t = step_device(); dev_ms += t[0]
     barrier()
     wall_s = time.time() - t_wall0
-    launches = solver.launch_count() * args.steps
+    launches = solver.launch_count() * args.steps; graph_launches = solver.graph_launch_count() * args.steps
     # per-phase device times (and the backward-pass launch duration for the roofline) need the phases un-overlapped:
     # a second, shorter pass with one problem group, every phase bracketed by CUDA events on the launch stream
     solver.set_groups(1)
@@ -227,6 +255,38 @@ def main():
     barrier()
     e2e_s = time.time() - t0
     clocks = sampler.stop()
+    # strong scaling (BASELINE configs[3]): a FIXED global batch of 512 problems split over the ranks, same timing rules; on one GPU
+    # this is the 512-problem single-GPU figure the N-GPU values are divided by
+    strong = None
+    if not BENCH_EE and os.environ.get("PDDP_BENCH_STRONG", "1") != "0" and STRONG_BATCH % world == 0:
+        sb = STRONG_BATCH // world
+        s2 = pddp.Solver(pddp.default_config_kuka(N, sb, device=local_rank, tol_cost=0.0))
+        lo2, hi2 = sharding.shard_range(rank, world, STRONG_BATCH)
+        a0, b0_, g0 = pddp.make_inputs_kuka(N, hi2 - lo2, seed0=lo2)
+        e_x0 = torch.from_numpy(a0).to(dev); e_u0 = torch.from_numpy(b0_).to(dev); e_xg = torch.from_numpy(g0).to(dev)
+        e_x = torch.empty_like(e_x0); e_u = torch.empty_like(e_u0)
+        e_J = torch.empty((sb, L1), dtype=torch.float32, device=dev); e_a = torch.empty((sb, L1), dtype=torch.int32, device=dev); e_it = torch.empty(sb, dtype=torch.int32, device=dev)
+        t2 = np.zeros(6, np.float64); nst = max(2, args.steps // 2)
+
+        def step_strong():
+            flush.fill_(1); torch.cuda.synchronize()
+            s2.solve_device(e_x0.data_ptr(), e_u0.data_ptr(), e_xg.data_ptr(), e_x.data_ptr(), e_u.data_ptr(), e_J.data_ptr(), e_a.data_ptr(), e_it.data_ptr(), 1, t2)
+            return t2[0]
+        for _ in range(3):
+            step_strong()
+        barrier(); ms2 = 0.0
+        for _ in range(nst):
+            ms2 += step_strong()
+        barrier()
+        st2 = torch.tensor([ms2, float(int(e_it.sum().item()) * nst)], dtype=torch.float64, device=dev)
+        if world > 1:
+            m2 = st2.clone(); dist.all_reduce(m2, op=dist.ReduceOp.MAX); q2 = st2.clone(); dist.all_reduce(q2, op=dist.ReduceOp.SUM)
+            ms2, it2 = m2[0].item(), q2[1].item()
+        else:
+            it2 = st2[1].item()
+        strong = {"global_batch": STRONG_BATCH, "batch_per_gpu": sb, "n_gpus": world, "value": it2 / (ms2 / 1000.0), "unit": UNIT, "steps": nst,
+                  "ms_per_step": ms2 / nst, "scaling": "strong", "note": "the 1-GPU run of this leg is the denominator of the N-GPU speed-up"}
+        s2.freeMemory_GPU(); del e_x0, e_u0, e_xg, e_x, e_u, e_J, e_a, e_it
     h2d = x0.nbytes + u0.nbytes + xg.nbytes
     d2h = o["x"].nbytes + o["u"].nbytes + o["Jout"].nbytes + o["alphaOut"].nbytes + o["iters"].nbytes
     stats = torch.tensor([dev_ms, e2e_s, float(iters_rank), float(e2e_iters), phase[3]], dtype=torch.float64, device=dev)
@@ -249,7 +309,7 @@ def main():
                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": dict(CONFIG, global_batch=B * world, parallelism=f"problem-sharded x{world}", stream_groups_per_gpu=groups),
                "e2e": {"value": e2e_iters_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-               "gpu_launches": launches, "clocks": clocks,
+               "gpu_launches": launches, "graph_launches": graph_launches, "clocks": clocks,
                "roofline": {"kernel": "bp_kernel<14,7>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": None, "peak_source": peak_src, "avg_launch_us": bp_avg_s * 1e6, "problems_per_launch": B,
                             "algorithmic_bytes_per_problem": BP_BYTES_PER_PROBLEM},
@@ -268,11 +328,23 @@ def main():
              "frac": sim_flop / (ph["sim+select"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"},
             {"kernel": "nis_kernel", "bound": "fp32 issue / latency", "achieved": nis_flop / (ph["nis"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
              "frac": nis_flop / (ph["nis"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"}]
+        # DRAM traffic of the backward pass: one ncu --set full capture per kernel version (tools/gpu_bp_traffic.sh), not something a bench
+        # run can measure itself; the capture records the hash of the kernel source it was taken from, and a capture of an older
+        # source is reported as stale instead of passing for the current kernel
         ncu = os.path.join(ROOT, "profiles", "bp_traffic.json")
         if os.path.exists(ncu):
-            out["roofline"]["traffic"] = json.load(open(ncu)).get("dram_bytes_per_launch")
+            tr = json.load(open(ncu)); cur = kernel_source_hash()
+            out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
+            out["roofline"]["traffic_source"] = {"file": "profiles/bp_traffic.json", "captured_from_source_sha1": tr.get("kernel_source_sha1"),
+                                                 "current_source_sha1": cur, "stale": tr.get("kernel_source_sha1") != cur}
+        if strong is not None:
+            out["strong"] = strong
         if world == 1:
             out["cpu_baseline"] = cpu_baseline()
+            rg = ref_gpu_run()
+            if rg:
+                rg["speedup_value"] = value / rg["value"]; rg["speedup_e2e"] = out["e2e"]["value"] / rg["value"]
+                out["reference_gpu"] = rg
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -176,6 +176,15 @@ int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, d
  * problem's final trajectory, [batch] floats (HOST) */
 int pddp_final_max_defect(pddp_handle h, float *max_d);
 
+/* Device-resident iteration loop (DDPWrappers.cuh:52-114 is a host loop with >= 10 synchronisations per iteration):
+ * the iterations of a solve are replayed from CUDA graphs of `iterations_per_graph` iterations each (default 10, env PDDP_GRAPH_CHUNK),
+ * captured at the first solve of a shape; with TOL_COST > 0 the host polls the number of unfinished problems between graphs.  On by
+ * default (env PDDP_GRAPHS=0 / on = 0: plain stream launches).  A solve that asks for per-phase times with one problem group is timed
+ * launch by launch instead.  pddp_last_graph_launch_count: graphs launched by the last solve (pddp_last_launch_count counts the kernels
+ * inside them). */
+int pddp_set_graphs(pddp_handle h, int on, int iterations_per_graph);
+long pddp_last_graph_launch_count(pddp_handle h);
+
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);
 

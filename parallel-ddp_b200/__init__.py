@@ -46,7 +46,7 @@ EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
            "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
            "pddp_default_config", "pddp_plant_dims", "pddp_register_plant", "pddp_load_plant_library", "pddp_plant_error", "pddp_make_inputs",
-           "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect",
+           "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect", "pddp_set_graphs", "pddp_last_graph_launch_count",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -102,6 +102,8 @@ def load_library():
     L.pddp_make_inputs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint, FP, FP, FP]
     L.pddp_last_iteration_times.argtypes = [H, DP, DP, DP, DP, C.c_int]
     L.pddp_final_max_defect.argtypes = [H, FP]
+    L.pddp_set_graphs.argtypes = [H, C.c_int, C.c_int]
+    L.pddp_last_graph_launch_count.argtypes = [H]; L.pddp_last_graph_launch_count.restype = C.c_long
     L.pddp_unit_integrator.argtypes = [H, FP, FP, C.c_int, FP]
     L.pddp_unit_cost.argtypes = [H, FP, FP, FP, IP, C.c_int, FP, FP, FP]
     _lib = L
@@ -312,6 +314,13 @@ class Solver:
         d = np.zeros(self.cfg.batch, np.float32)
         self._ck(self.L.pddp_final_max_defect(self.h, d.ctypes.data_as(FP)), "pddp_final_max_defect")
         return d
+
+    def set_graphs(self, on, iterations_per_graph=0):
+        """CUDA-graph replay of the iteration loop (default on, 10 iterations per graph)"""
+        self._ck(self.L.pddp_set_graphs(self.h, int(on), int(iterations_per_graph)), "pddp_set_graphs")
+
+    def graph_launch_count(self):
+        return int(self.L.pddp_last_graph_launch_count(self.h))
 
     def launch_count(self):
         return int(self.L.pddp_last_launch_count(self.h))

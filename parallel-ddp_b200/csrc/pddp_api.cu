@@ -43,6 +43,9 @@ struct pddp_solver {
     int *h_nactive = nullptr;
     cudaEvent_t ev[8];
     double last_ms = 0; int last_launches = 0;
+    struct GraphEntry { cudaGraphExec_t exec; long kernels; };
+    std::map<std::string, GraphEntry> graphs;                                  // captured iteration chunks, keyed by (device state, iterations, groups)
+    bool use_graphs = true; int graph_chunk = 10; long graph_launches = 0;
     std::vector<double> it_ms[4];                                              // per-iteration device times of the last timed solve: sim(+selection), sweep, bp, nis
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
     float *d_xTarget = nullptr;
@@ -172,6 +175,8 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     for (int g = 1; g < 8; g++){ cudaStream_t st; CKC(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)); h->gstreams.push_back(st); }
     for (int g = 0; g < 9; g++){ cudaEvent_t e; CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->gev.push_back(e); }
     { const char *env = std::getenv("PDDP_SKIP_UNCHANGED"); h->skip_env = env && std::atoi(env) != 0; }
+    { const char *env = std::getenv("PDDP_GRAPHS"); h->use_graphs = !(env && std::atoi(env) == 0); }
+    { const char *env = std::getenv("PDDP_GRAPH_CHUNK"); const int v = env ? std::atoi(env) : 0; if (v >= 1 && v <= 1000){ h->graph_chunk = v; } }
     { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 4; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S)); S.skip_unchanged = h->skip_env ? 1 : 0;
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
@@ -254,6 +259,7 @@ extern "C" void pddp_destroy(pddp_handle h){
     if (!h){ return; }
     cudaSetDevice(h->cfg.device);
     if (h->stream){ cudaStreamSynchronize(h->stream); }
+    for (auto &kv : h->graphs){ cudaGraphExecDestroy(kv.second.exec); }
     for (void *p : h->allocs){ cudaFree(p); }
     if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
     for (auto &e : h->ev){ if (e){ cudaEventDestroy(e); } }
@@ -366,9 +372,66 @@ static int launch_nis(pddp_handle h, cudaStream_t st, int b0, int nb){
 // the iteration loop of runiLQR_GPU (DDPWrappers.cuh:52-114) with all host decisions moved to select_kernel.
 // The batch is cut into `groups` problem groups, each on its own stream: problems are independent, so the latency-bound
 // kernels of one group (backward pass, sweep, selection) run under the throughput-bound ones (sim, nis) of another.
+// One iteration of problems [b0, b0+nb) on stream st: the five launches of the hot path
+static int launch_iteration(pddp_handle h, cudaStream_t st, int b0, int nb){
+    int rc;
+    if ((rc = launch_bp(h, st, b0, nb))){ return rc; }
+    if ((rc = launch_sweep(h, st, b0, nb))){ return rc; }
+    if ((rc = launch_sim(h, st, b0, nb))){ return rc; }
+    if ((rc = launch_select(h, st, b0, nb))){ return rc; }
+    return launch_nis(h, st, b0, nb);
+}
+// Device-resident iteration loop: `cnt` iterations of every problem group -- fork to the group streams, 5 x cnt launches per group,
+// join -- captured ONCE as a CUDA graph and replayed by every later solve of the same shape.  All decisions of an
+// iteration are taken on the device (select_kernel) and a finished problem's kernels return at their first instruction, so the graph
+// needs no host in the loop; only the convergence poll between chunks (TOL_COST > 0) comes back to the host.
+static int iteration_graph(pddp_handle h, int cnt, int groups, pddp_solver::GraphEntry *out){
+    DevState &S = h->S;
+    std::string key(reinterpret_cast<const char*>(&S), sizeof(S)); key += "#" + std::to_string(cnt) + "#" + std::to_string(groups);
+    auto it = h->graphs.find(key);
+    if (it != h->graphs.end()){ *out = it->second; return 0; }
+    if (h->graphs.size() >= 32){ for (auto &kv : h->graphs){ cudaGraphExecDestroy(kv.second.exec); } h->graphs.clear(); }
+    const long l0 = h->launches; int rc = 0;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    if (groups > 1){ cudaEventRecord(h->gev[8], h->stream); for (int g = 1; g < groups; g++){ cudaStreamWaitEvent(h->gstreams[g], h->gev[8], 0); } }
+    for (int i = 0; i < cnt && !rc; i++){
+        for (int g = 0; g < groups && !rc; g++){
+            const int b0 = (int)((long)S.B*g/groups), nb = (int)((long)S.B*(g+1)/groups) - b0;
+            rc = launch_iteration(h, h->gstreams[g], b0, nb);
+        }
+    }
+    for (int g = 1; g < groups; g++){ cudaEventRecord(h->gev[g], h->gstreams[g]); cudaStreamWaitEvent(h->stream, h->gev[g], 0); }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);             // always ends the capture, also after a failed launch
+    pddp_solver::GraphEntry ge{nullptr, h->launches - l0}; h->launches = l0;
+    if (rc){ if (graph){ cudaGraphDestroy(graph); } return rc; }
+    if (e != cudaSuccess || !graph){ h->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return PDDP_E_CUDA; }
+    const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess){ h->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2); return PDDP_E_CUDA; }
+    h->graphs[key] = ge; *out = ge;
+    return 0;
+}
+
 static int run_iterations(pddp_handle h, double *times_ms, int groups){
     DevState &S = h->S;
     const bool timing = times_ms != nullptr && groups == 1;
+    if (!timing && h->use_graphs){
+        if (times_ms){ times_ms[1] = times_ms[2] = times_ms[3] = times_ms[4] = 0.0; }
+        const bool poll_g = h->cfg.tol_cost > 0.0f;
+        for (int it0 = 0; it0 < S.iter_cap; it0 += h->graph_chunk){
+            const int cnt = (S.iter_cap - it0 < h->graph_chunk) ? S.iter_cap - it0 : h->graph_chunk;
+            pddp_solver::GraphEntry ge; int rc = iteration_graph(h, cnt, groups, &ge); if (rc){ return rc; }
+            CK(cudaGraphLaunch(ge.exec, h->stream));
+            h->launches += ge.kernels; h->graph_launches += 1;
+            if (poll_g && it0 + cnt < S.iter_cap){
+                CK(cudaMemcpyAsync(h->h_nactive, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+                if (*h->h_nactive == 0){ break; }
+            }
+        }
+        return 0;
+    }
     struct EventBag { std::vector<cudaEvent_t> v; ~EventBag(){ for (auto e : v){ cudaEventDestroy(e); } } } bag;     // released on every path out
     std::vector<cudaEvent_t> &evs = bag.v;
     auto mark = [&](){ if (timing){ cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, h->stream); evs.push_back(e); } };
@@ -386,7 +449,7 @@ static int run_iterations(pddp_handle h, double *times_ms, int groups){
             mark(); if ((rc = launch_nis(h, st, b0, nb))){ return rc; }
         }
         it_done = it + 1;
-        if (poll && (it % 4) == 3){
+        if (poll && ((it % 4) == 3 || (long long)S.B*S.A*S.M <= 4LL*h->num_sms)){       // small batches (the latency path): every iteration
             // convergence-driven early exit: read the active-problem counter once all groups reached this iteration
             for (int g = 1; g < groups; g++){ CK(cudaStreamSynchronize(h->gstreams[g])); }
             CK(cudaMemcpyAsync(h->h_nactive, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -418,12 +481,12 @@ extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *
     if (!h){ return PDDP_E_INVALID; }
     DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m; int rc;
     CK(cudaSetDevice(h->cfg.device));
-    h->launches = 0;
+    h->launches = 0; h->graph_launches = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = launch_reset(h, ignoreFirstDefectFlag, h->next_clear))){ return rc; }
     CK(cudaMemcpyAsync(S.xp, d_x0, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(S.up, d_u0, (size_t)B*N*m*4, cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(S.xGoal, d_xGoal, (size_t)B*n*4, cudaMemcpyDeviceToDevice, h->stream));
+    if (d_xGoal != S.xGoal){ CK(cudaMemcpyAsync(S.xGoal, d_xGoal, (size_t)B*n*4, cudaMemcpyDeviceToDevice, h->stream)); }      // pddp_solve uploads straight into S.xGoal
     if ((rc = launch_init(h, h->next_rollout))){ return rc; }
     h->next_clear = 1; h->next_rollout = 0;          // the flags apply to one solve
     CK(cudaEventRecord(h->ev[1], h->stream));
@@ -551,7 +614,7 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m, L = S.max_iter + 1; int rc;
     if (max_iter < 1 || max_iter > S.max_iter){ h->err = "max_iter of the step must be in [1, config max_iter]"; return PDDP_E_INVALID; }
     CK(cudaSetDevice(h->cfg.device));
-    h->launches = 0;
+    h->launches = 0; h->graph_launches = 0;
     std::vector<int> flags(3*(size_t)B);
     for (int b = 0; b < B; b++){
         if (shiftAmount[b] < 0){ h->err = "negative shiftAmount"; return PDDP_E_INVALID; }
@@ -739,6 +802,12 @@ extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
     return e == cudaSuccess ? 0 : PDDP_E_CUDA;
 }
 extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
+extern "C" long pddp_last_graph_launch_count(pddp_handle h){ return h ? h->graph_launches : 0; }
+extern "C" int pddp_set_graphs(pddp_handle h, int on, int iterations_per_graph){
+    if (!h || iterations_per_graph < 0 || iterations_per_graph > 1000){ return PDDP_E_INVALID; }
+    h->use_graphs = on != 0; if (iterations_per_graph > 0){ h->graph_chunk = iterations_per_graph; }
+    return 0;
+}
 // per-iteration device times (ms) of the last solve that was given a times_ms array and ran as one problem group: what the reference
 // stores in its simTime / sweepTime / bpTime / nisTime arrays (DDPWrappers.cuh:60-107; there: host clock around each phase)
 extern "C" int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, double *bp_ms, double *nis_ms, int capacity){

@@ -1,7 +1,8 @@
 """Trajectory hand-off format: drake::lcmt_trajectory_f as the reference's MPC loop publishes it
 (LCMHelpers.cuh:245-256).  The golden bytes were produced by the reference's own generated type
-(lcmtypes/drake/lcmt_trajectory_f.hpp) in oracle/ref_harness/ref_lcm_traj.cpp; the LCM core primitives under it are a
-stand-in (third-party lcm_coretypes.h is absent: that part of the parity is unpinned, see oracle/ref_harness/lcm_stub)."""
+(lcmtypes/drake/lcmt_trajectory_f.hpp) in oracle/ref_harness/ref_lcm_traj.cpp over a stand-in for the absent third-party
+lcm_coretypes.h (oracle/ref_harness/lcm_stub); the byte order of the primitives themselves is pinned by a known-answer vector written from
+LCM's published type specification (test_primitives_follow_the_published_lcm_encoding)."""
 import importlib
 import os
 import sys
@@ -40,6 +41,27 @@ def test_pack_matches_reference_bytes(fb):
         assert dx.size == 14 * N * 4 and np.array_equal(dx[:14 * N], x) and dk.size == 98 * N * 4 and np.array_equal(dk[:98 * N], KT)
     else:
         assert dx.size == 0 and dk.size == 0
+
+
+def test_primitives_follow_the_published_lcm_encoding():
+    """Known-answer vector for the LCM core primitives under the message type.  The LCM type specification (lcm-proj/lcm,
+    docs/content/lcm-type-ref.md, "Primitives": `int32_t`, `int64_t` two's complement and `float` IEEE 754 binary32, all in network byte
+    order; a message starts with its 8-byte fingerprint, members follow in declaration order with no padding, a variable-length array is
+    its elements back to back, its length being the int32 member declared for it) fixes the bytes of this message by hand:
+        utime = 0x0102030405060708, x = [1.0, -2.0], u = [0.5], KT = []
+    The reference's library copy (lcm/lcm_coretypes.h) is absent, so this vector -- not the stand-in header of the harness -- is what pins
+    the byte order of the primitives."""
+    x = np.array([1.0, -2.0], np.float32); u = np.array([0.5], np.float32); k = np.zeros(0, np.float32)
+    import ctypes as C
+    L = pddp.load_library(); need = L.pddp_traj_f_encoded_size(2, 1, 0); buf = (C.c_ubyte * need)()
+    assert L.pddp_traj_f_encode(0x0102030405060708, x.ctypes.data_as(pddp.FP), 2, u.ctypes.data_as(pddp.FP), 1, None, 0, buf, need) == need
+    h = 0x8fb839bd5c6031ee; fp = ((h << 1) & 0xFFFFFFFFFFFFFFFF) + (h >> 63)            # lcmt_trajectory_f.hpp:256-260
+    expect = (fp.to_bytes(8, "big") + bytes([1, 2, 3, 4, 5, 6, 7, 8])                     # int64 utime
+              + bytes([0, 0, 0, 2]) + bytes([0, 0, 0, 1]) + bytes([0, 0, 0, 0])           # int32 x_size, u_size, KT_size
+              + bytes([0x3F, 0x80, 0, 0]) + bytes([0xC0, 0, 0, 0]) + bytes([0x3F, 0, 0, 0]))   # 1.0f, -2.0f, 0.5f
+    assert bytes(buf) == expect
+    t, dx, du, dk = pddp.traj_f_decode(expect)
+    assert t == 0x0102030405060708 and np.array_equal(dx, x) and np.array_equal(du, u) and dk.size == 0
 
 
 def test_encode_decode_round_trip_and_errors():
