@@ -18,6 +18,7 @@
 #include "plant_kuka.cuh"
 
 #include "dev_state.cuh"
+#include "bp_warp.cuh"
 namespace pddp {
 
 // ------------------------------------------------------------------------------------------------------------------

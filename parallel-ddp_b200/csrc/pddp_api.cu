@@ -50,7 +50,8 @@ struct pddp_solver {
     size_t smem_bp, smem_sweep, smem_sim, smem_sel, smem_nis, smem_udyn, smem_ugrad;
     float *d_xTarget = nullptr;
     int *d_cost_shift = nullptr; bool use_cost_shift = false;
-    int sim_lanes = 16;                                                        // lanes per simulated trajectory (16: throughput shape, 32: latency shape)
+    int sim_lanes = 16;
+    int bp_shape = 0;                                                          // backward pass (env PDDP_BP_SHAPE): 0 = by launch size, 1 = warp chains (bp_warp.cuh), 2 = block-cooperative (kernels.cuh)                                                        // lanes per simulated trajectory (16: throughput shape, 32: latency shape)
     std::map<std::string, std::pair<void*, size_t>> arrays;
 };
 
@@ -238,6 +239,8 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
         h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
         h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
         CKC(cudaFuncSetAttribute(bp_kernel<kuka::NX, kuka::NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bp));
+        CKC(cudaFuncSetAttribute(bp_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BPW_WARPS*sizeof(BpWarpSmem))));
+        { const char *env = std::getenv("PDDP_BP_SHAPE"); h->bp_shape = env ? std::atoi(env) : 0; }
         CKC(cudaFuncSetAttribute(sweep_kernel<kuka::NX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sweep));
         CKC(cudaFuncSetAttribute(sim_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
         CKC(cudaFuncSetAttribute(sim_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_sim));
@@ -341,7 +344,15 @@ static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInit
 static int launch_bp(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
     if (h->ops){ CKP(h->ops->launch_bp(&S, st, b0, nb)); h->launches += 1; return 0; }
-    bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_CTA, h->smem_bp, st>>>(S, b0);
+    // two shapes with identical arithmetic: warp chains (20 resident chains per SM, no barriers) win once the launch holds several
+    // chains per SM; below that a chain's latency is what counts and the block-cooperative kernel (8 warps per chain) is ~2x quicker
+    const bool warp_chains = h->bp_shape == 1 || (h->bp_shape == 0 && (long long)nb*S.M >= 4LL*h->num_sms);
+    if (warp_chains){
+        const int nchains = nb*S.M;
+        bp_warp_kernel<<<(nchains + BPW_WARPS - 1)/BPW_WARPS, 32*BPW_WARPS, BPW_WARPS*sizeof(BpWarpSmem), st>>>(S, b0, nchains);
+    } else {
+        bp_kernel<kuka::NX, kuka::NU><<<nb*S.M, BP_CTA, h->smem_bp, st>>>(S, b0);
+    }
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){

