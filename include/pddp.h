@@ -176,6 +176,20 @@ int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, d
  * problem's final trajectory, [batch] floats (HOST) */
 int pddp_final_max_defect(pddp_handle h, float *max_d);
 
+/* ---- line search sharded over GPUs (SURVEY 8e second paragraph; north_star "a single NCCL exchange at line-search selection").
+ * One process per GPU, every rank owns a handle of the SAME configuration and calls pddp_solve* with the SAME inputs.  After
+ * pddp_alpha_shard_init a solve runs like this on every rank: backward pass and next-iteration setup replicated, forward sweep and
+ * simulation only for the rank's n_alpha / nranks step sizes, then ONE ncclAllGather of the (J, defect) pairs of all step sizes, the
+ * reference's sequential scan (fpHelpers.cuh:395-408) on identical data on every rank -- so the chosen step size, the rho schedule and
+ * the exit decisions are those of the unsharded solve bit for bit --, and the accepted candidate handed from its owner to the others
+ * (ncclAllReduce of its bit patterns, 4 N (2n+m) bytes per problem).  NCCL is bound with dlopen("libnccl.so.2") when this is called.
+ *   pddp_alpha_shard_unique_id: 128 bytes (ncclUniqueId) made by rank 0 and given to all ranks by the caller (any transport)
+ *   pddp_alpha_shard_stats: mean device time of the two collectives per iteration (us, sampled every 8th iteration) and the rank's range
+ * Cold starts of the joint-space cost on PLANT 4 only; n_alpha must be a multiple of nranks. */
+int pddp_alpha_shard_unique_id(void *id128);
+int pddp_alpha_shard_init(pddp_handle h, int rank, int nranks, const void *id128);
+int pddp_alpha_shard_stats(pddp_handle h, double *exchange_us_per_iteration, int *a_first, int *a_cnt);
+
 /* Device-resident iteration loop (DDPWrappers.cuh:52-114 is a host loop with >= 10 synchronisations per iteration):
  * the iterations of a solve are replayed from CUDA graphs of `iterations_per_graph` iterations each (default 10, env PDDP_GRAPH_CHUNK),
  * captured at the first solve of a shape; with TOL_COST > 0 the host polls the number of unfinished problems between graphs.  On by
@@ -184,6 +198,10 @@ int pddp_final_max_defect(pddp_handle h, float *max_d);
  * inside them). */
 int pddp_set_graphs(pddp_handle h, int on, int iterations_per_graph);
 long pddp_last_graph_launch_count(pddp_handle h);
+
+/* Shape of the backward pass of PLANT 4: 0 = chosen by launch size (default, env PDDP_BP_SHAPE), 1 = warp chains (bp_warp.cuh), 2 = block-
+ * cooperative (kernels.cuh).  Identical results. */
+int pddp_set_bp_shape(pddp_handle h, int shape);
 
 /* number of kernels launched by the last pddp_solve* call on this handle */
 long pddp_last_launch_count(pddp_handle h);

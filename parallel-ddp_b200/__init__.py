@@ -46,7 +46,7 @@ EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
            "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
            "pddp_default_config", "pddp_plant_dims", "pddp_register_plant", "pddp_load_plant_library", "pddp_plant_error", "pddp_make_inputs",
-           "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect", "pddp_set_graphs", "pddp_last_graph_launch_count",
+           "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect", "pddp_set_graphs", "pddp_last_graph_launch_count", "pddp_alpha_shard_unique_id", "pddp_alpha_shard_init", "pddp_alpha_shard_stats", "pddp_set_bp_shape",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
 
 _lib = None
@@ -103,6 +103,10 @@ def load_library():
     L.pddp_last_iteration_times.argtypes = [H, DP, DP, DP, DP, C.c_int]
     L.pddp_final_max_defect.argtypes = [H, FP]
     L.pddp_set_graphs.argtypes = [H, C.c_int, C.c_int]
+    L.pddp_alpha_shard_unique_id.argtypes = [C.c_void_p]
+    L.pddp_alpha_shard_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
+    L.pddp_alpha_shard_stats.argtypes = [H, DP, IP, IP]
+    L.pddp_set_bp_shape.argtypes = [H, C.c_int]
     L.pddp_last_graph_launch_count.argtypes = [H]; L.pddp_last_graph_launch_count.restype = C.c_long
     L.pddp_unit_integrator.argtypes = [H, FP, FP, C.c_int, FP]
     L.pddp_unit_cost.argtypes = [H, FP, FP, FP, IP, C.c_int, FP, FP, FP]
@@ -154,6 +158,14 @@ def make_inputs(plant, N, batch, seed0=0):
     if L.pddp_make_inputs(plant, N, batch, seed0, x0.ctypes.data_as(FP), u0.ctypes.data_as(FP), xg.ctypes.data_as(FP)) != 0:
         raise PddpError(f"no example inputs for PLANT {plant}")
     return x0, u0, xg
+
+
+def alpha_shard_unique_id():
+    """128-byte NCCL unique id for Solver.alpha_shard_init (call on rank 0, hand to all ranks)"""
+    L = load_library(); buf = (C.c_ubyte * 128)()
+    if L.pddp_alpha_shard_unique_id(buf) != 0:
+        raise PddpError("pddp_alpha_shard_unique_id: libnccl.so.2 could not be loaded")
+    return bytes(buf)
 
 
 def _f(a):
@@ -314,6 +326,21 @@ class Solver:
         d = np.zeros(self.cfg.batch, np.float32)
         self._ck(self.L.pddp_final_max_defect(self.h, d.ctypes.data_as(FP)), "pddp_final_max_defect")
         return d
+
+    def set_bp_shape(self, shape):
+        """backward-pass shape: 0 by launch size, 1 warp chains, 2 block-cooperative (identical results)"""
+        self._ck(self.L.pddp_set_bp_shape(self.h, int(shape)), "pddp_set_bp_shape")
+
+    def alpha_shard_init(self, rank, nranks, unique_id):
+        """shard the line search's step sizes over `nranks` GPUs (one process each); unique_id: the 128 bytes of alpha_shard_unique_id()
+        made on rank 0 and handed to every rank"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.L.pddp_alpha_shard_init(self.h, int(rank), int(nranks), buf), "pddp_alpha_shard_init")
+
+    def alpha_shard_stats(self):
+        us = C.c_double(); a0 = C.c_int(); cnt = C.c_int()
+        self.L.pddp_alpha_shard_stats(self.h, C.byref(us), C.byref(a0), C.byref(cnt))
+        return dict(exchange_us_per_iteration=us.value, a_first=a0.value, a_cnt=cnt.value)
 
     def set_graphs(self, on, iterations_per_graph=0):
         """CUDA-graph replay of the iteration loop (default on, 10 iterations per graph)"""

@@ -50,6 +50,11 @@ struct DevState {
     int *init_knot;                // [B] EE_COST quirk of the receding-horizon path, see select_kernel mode 1 (0 everywhere else)
     const float *xTarget;          // [B][n] or null: the nominal-state terms measure x from it (receding-horizon path, MPCHelpers.cuh:900)
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE, Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;
+    // step-size sharding of the line search over ranks (pddp_alpha_shard_init): this rank sweeps / simulates candidates
+    // a_first .. a_first + a_cnt - 1 (all of them without sharding); the per-candidate (J, defect) pairs travel through xchg_send ->
+    // ncclAllGather -> xchg_recv [rank][B][a_cnt][2], the accepted candidate through acc_buf [B][N*(2n+m)] (ncclAllReduce of its bits)
+    int a_first, a_cnt;
+    float *xchg_send, *xchg_recv; int *acc_buf;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -96,7 +101,7 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
     __shared__ unsigned long long full[SWEEP_SLOTS];
     SweepSlot<n> *slots = reinterpret_cast<SweepSlot<n>*>(sw_raw);
     // `splits` CTAs share one problem (each takes A/splits step sizes) so that a small batch still covers the SMs
-    const int b = b0 + blockIdx.x / splits, a0 = (blockIdx.x % splits)*(S.A / splits), N = S.N, NBF = N / S.M;
+    const int b = b0 + blockIdx.x / splits, a0 = S.a_first + (blockIdx.x % splits)*(S.a_cnt / splits), N = S.N, NBF = N / S.M;
     if (S.done[b]){ return; }
     // The problem's sequence ((A - BK), B du, xp, d per knot) streams through a ring of SWEEP_SLOTS slices of SWEEP_CH knots,
     // each filled by four TMA bulk copies on its own mbarrier.  The recursion starts as soon as the first slice has landed; a
@@ -119,7 +124,7 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
         for (int c = 0; c < SWEEP_SLOTS && c < nslices; c++){ issue(c); }
     }
     __syncthreads();
-    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;       // blockDim = 32 * (A / splits): every warp has a step size
+    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;       // blockDim = 32 * (a_cnt / splits): every warp has a step size
     const float alpha = S.alpha[a];
     float *gx = S.x + ((size_t)b*S.A + a)*N*n;
     mbar_wait(&full[0], 0);

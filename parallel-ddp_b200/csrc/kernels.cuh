@@ -466,7 +466,7 @@ __device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const f
 // LANES = 32: one candidate per warp, the latency shape for small batches (fewer passes per phase: 13 % faster per knot when the
 // whole launch fits the machine with one warp per scheduler).  Same arithmetic either way; the host picks (launch_sim_any).
 template <bool EE, int LANES>
-__global__ void sim_kernel(DevState S, int b0, int n_cand){
+__global__ void sim_kernel(DevState S, int b0, int n_cand, int a_first){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, GPW = 32 / LANES;
     float *sI = reinterpret_cast<float*>(smem_raw);            // 252
@@ -484,6 +484,7 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand){
     int a = (blockIdx.x % apb)*GPW + grp;
     const bool live = a < n_cand;                              // odd count: the last half-warp replays the last candidate without storing
     if (!live){ a = n_cand - 1; }
+    a += a_first;                                              // candidates a_first .. a_first + n_cand - 1 (step-size sharding)
     SimGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
@@ -586,10 +587,19 @@ __global__ void select_kernel(DevState S, int mode, int b0){
     extern __shared__ __align__(16) float ssel[];          // [A][N] costs + [A] J + [A] dT
     const int b = b0 + blockIdx.x, N = S.N, A = S.A, n = S.n;
     if (S.done[b]){ return; }
-    const int a = threadIdx.x >> 5, l = threadIdx.x & 31;
+    // mode 2 / 3 (step-size sharding): 2 = this rank's candidates only, their (J, defect) pairs go to the exchange buffer and the kernel
+    // ends; 3 = the pairs of all candidates come back from the all-gather and the selection below runs, identically on every rank
+    const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int a = (mode == 2) ? S.a_first + wi : wi;
     float *sJ = ssel + (size_t)A*N, *sdT = sJ + A;
-    const int nA = (mode == 1) ? 1 : A;
-    if (a < nA){
+    const int nA = (mode == 1) ? 1 : (mode == 2 ? S.a_first + S.a_cnt : A);
+    if (mode == 3){
+        if (threadIdx.x < A){
+            const int r = threadIdx.x / S.a_cnt, i = threadIdx.x % S.a_cnt;
+            const float *pr = S.xchg_recv + (((size_t)r*S.B + b)*S.a_cnt + i)*2;
+            sJ[threadIdx.x] = pr[0]; sdT[threadIdx.x] = pr[1];
+        }
+    } else if (a < nA){
         float *v = ssel + (size_t)a*N; const float *gc = S.costk + ((size_t)b*A + a)*N;
         if (S.ee && (mode == 0 || S.rolled_out)){
             // costKern<T,0> (fpHelpers.cuh:165-172): the simulation's per-interval partials, summed in interval order
@@ -605,7 +615,7 @@ __global__ void select_kernel(DevState S, int mode, int b0){
         }
         // defect: max over the M-1 interval boundaries of the L1 norm (fpHelpers.cuh:94-111)
         float dmax = 0.f;
-        if (mode == 0 && l < S.M - 1){
+        if ((mode == 0 || mode == 2) && l < S.M - 1){
             const int NBF = N / S.M; const float *dk = S.d + (((size_t)b*A + a)*N + (l+1)*NBF - 1)*n;
             float acc = 0.f; for (int c = 0; c < n; c++){ acc = ADD(acc, fabsf(dk[c])); }
             dmax = acc;
@@ -614,6 +624,10 @@ __global__ void select_kernel(DevState S, int mode, int b0){
         if (l == 0){ sdT[a] = dmax; }
     }
     __syncthreads();
+    if (mode == 2){
+        if (l == 0 && wi < S.a_cnt){ float *ps = S.xchg_send + ((size_t)b*S.a_cnt + wi)*2; ps[0] = sJ[a]; ps[1] = sdT[a]; }
+        return;
+    }
     if (threadIdx.x != 0){ return; }
     float *Jout = S.Jout + (size_t)b*(S.max_iter+1); int *alphaOut = S.alphaOut + (size_t)b*(S.max_iter+1);
     if (mode == 1){
@@ -788,6 +802,32 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
         const int ky = e / n, kx = e % n;
         const float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
         gAB[e] = FMA(dt, dxd, (ky == kx) ? 1.f : 0.f);
+    }
+}
+
+// step-size sharding: the accepted candidate travels from the rank that simulated it to all others as an all-reduce (integer sum) of
+// its bit patterns -- every other rank contributes zeros, so the values arrive bit for bit.  pack: owner -> acc_buf, others zero;
+// unpack (after the all-reduce): acc_buf -> the candidate's slot of x, u, d on every rank.
+__global__ void ashard_pack_kernel(DevState S){
+    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m, a = S.alphaIndex[b], per = N*(2*n + m);
+    int *dst = S.acc_buf + (size_t)b*per;
+    const bool mine = S.accepted[b] && a >= S.a_first && a < S.a_first + S.a_cnt;
+    const int *sx = reinterpret_cast<const int*>(S.x + ((size_t)b*S.A + a)*N*n), *su = reinterpret_cast<const int*>(S.u + ((size_t)b*S.A + a)*N*m),
+              *sd = reinterpret_cast<const int*>(S.d + ((size_t)b*S.A + a)*N*n);
+    for (int i = threadIdx.x; i < per; i += blockDim.x){
+        int v = 0;
+        if (mine){ v = i < N*n ? sx[i] : (i < N*(n+m) ? su[i - N*n] : sd[i - N*(n+m)]); }
+        dst[i] = v;
+    }
+}
+__global__ void ashard_unpack_kernel(DevState S){
+    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m, a = S.alphaIndex[b], per = N*(2*n + m);
+    if (!S.accepted[b] || (a >= S.a_first && a < S.a_first + S.a_cnt)){ return; }
+    const int *src = S.acc_buf + (size_t)b*per;
+    int *dx = reinterpret_cast<int*>(S.x + ((size_t)b*S.A + a)*N*n), *du = reinterpret_cast<int*>(S.u + ((size_t)b*S.A + a)*N*m), *dd = reinterpret_cast<int*>(S.d + ((size_t)b*S.A + a)*N*n);
+    for (int i = threadIdx.x; i < per; i += blockDim.x){
+        const int v = src[i];
+        if (i < N*n){ dx[i] = v; } else if (i < N*(n+m)){ du[i - N*n] = v; } else { dd[i - N*(n+m)] = v; }
     }
 }
 

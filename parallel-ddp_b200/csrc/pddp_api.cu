@@ -7,6 +7,7 @@
 #include "kuka_model_data.inc"
 
 #include <cmath>
+#include <nccl.h>
 #include <dlfcn.h>
 #include <mutex>
 #include <cstdio>
@@ -51,6 +52,16 @@ struct pddp_solver {
     float *d_xTarget = nullptr;
     int *d_cost_shift = nullptr; bool use_cost_shift = false;
     int sim_lanes = 16;
+    // step-size sharding (pddp_alpha_shard_init): NCCL is bound at run time (dlopen), so single-GPU users do not need it
+    struct Nccl {
+        void *lib = nullptr; ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+        ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+        ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+        ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+        const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    } nccl;
+    cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr}; double xchg_ms = 0; long xchg_calls = 0;      // device time spent in the two collectives
     int bp_shape = 0;                                                          // backward pass (env PDDP_BP_SHAPE): 0 = by launch size, 1 = warp chains (bp_warp.cuh), 2 = block-cooperative (kernels.cuh)                                                        // lanes per simulated trajectory (16: throughput shape, 32: latency shape)
     std::map<std::string, std::pair<void*, size_t>> arrays;
 };
@@ -190,6 +201,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.exp_red_min = cfg->exp_red_min; S.exp_red_max = cfg->exp_red_max; S.max_defect = cfg->max_defect;
     S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2; S.grav = cfg->gravity;
     S.ee = cfg->ee_cost ? 1 : 0;
+    S.a_first = 0; S.a_cnt = A;
     S.Q_EE1 = cfg->Q_EE1; S.Q_EE2 = cfg->Q_EE2; S.QF_EE1 = cfg->QF_EE1; S.QF_EE2 = cfg->QF_EE2; S.R_EE = cfg->R_EE;
     S.Q_xdEE = cfg->Q_xdEE; S.QF_xdEE = cfg->QF_xdEE; S.Q_xEE = cfg->Q_xEE; S.QF_xEE = cfg->QF_xEE;
     float *dI, *dTb, *dal;
@@ -263,6 +275,8 @@ extern "C" void pddp_destroy(pddp_handle h){
     cudaSetDevice(h->cfg.device);
     if (h->stream){ cudaStreamSynchronize(h->stream); }
     for (auto &kv : h->graphs){ cudaGraphExecDestroy(kv.second.exec); }
+    if (h->nccl.comm && h->nccl.CommDestroy){ h->nccl.CommDestroy(h->nccl.comm); }
+    for (auto &e : h->xev){ if (e){ cudaEventDestroy(e); } }
     for (void *p : h->allocs){ cudaFree(p); }
     if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
     for (auto &e : h->ev){ if (e){ cudaEventDestroy(e); } }
@@ -310,13 +324,13 @@ static int launch_reset(pddp_handle h, int ignore_first, int clear){
 }
 #define CKP(call) do { const int e_ = (call); if (e_){ h->err = std::string(#call) + ": " + cudaGetErrorString((cudaError_t)e_); return PDDP_E_CUDA; } } while (0)
 // forward simulation of n_cand candidates of problems [b0, b0+nb): cost variant and lane shape picked here
-static void launch_sim_any(pddp_handle h, cudaStream_t st, int b0, int nb, int n_cand){
+static void launch_sim_any(pddp_handle h, cudaStream_t st, int b0, int nb, int n_cand, int a_first = 0){
     DevState &S = h->S;
     if (h->ops){ h->ops->launch_sim(&S, st, b0, nb, n_cand); return; } const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw), cta = 32*S.M;
     if (h->sim_lanes == 32){
-        if (S.ee){ sim_kernel<true, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); } else { sim_kernel<false, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); }
+        if (S.ee){ sim_kernel<true, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); } else { sim_kernel<false, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); }
     } else {
-        if (S.ee){ sim_kernel<true, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); } else { sim_kernel<false, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand); }
+        if (S.ee){ sim_kernel<true, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); } else { sim_kernel<false, 16><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); }
     }
 }
 static int launch_init(pddp_handle h, int rollout){       // initAlgGPU (nisInitHelpers.cuh:353-397), trajectory already in xp/up
@@ -359,13 +373,13 @@ static int launch_sweep(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S; if (S.M == 1){ return 0; }
     if (h->ops){ CKP(h->ops->launch_sweep(&S, st, b0, nb, h->num_sms)); h->launches += 1; return 0; }
     // enough CTAs to cover the SMs: split the step sizes of one problem over up to A CTAs (power-of-two divisor of A)
-    int splits = 1; while (nb*splits*2 <= h->num_sms && (S.A % (splits*2)) == 0){ splits *= 2; }
-    sweep_kernel<kuka::NX><<<nb*splits, 32*(S.A/splits), h->smem_sweep, st>>>(S, splits, b0);
+    int splits = 1; while (nb*splits*2 <= h->num_sms && (S.a_cnt % (splits*2)) == 0){ splits *= 2; }
+    sweep_kernel<kuka::NX><<<nb*splits, 32*(S.a_cnt/splits), h->smem_sweep, st>>>(S, splits, b0);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_sim(pddp_handle h, cudaStream_t st, int b0, int nb){
     DevState &S = h->S;
-    launch_sim_any(h, st, b0, nb, S.A);
+    launch_sim_any(h, st, b0, nb, S.a_cnt, S.a_first);
     h->launches += 1; CK(cudaGetLastError()); return 0;
 }
 static int launch_select(pddp_handle h, cudaStream_t st, int b0, int nb){
@@ -424,8 +438,47 @@ static int iteration_graph(pddp_handle h, int cnt, int groups, pddp_solver::Grap
     return 0;
 }
 
+// Iteration loop with the line search sharded over ranks (north_star): every rank holds the whole problem, runs the backward
+// pass and the next-iteration setup itself, but sweeps and simulates only ITS step sizes.  One exchange at selection: an all-gather of the
+// (J, defect) pairs of all step sizes, after which every rank runs the reference's sequential scan (fpHelpers.cuh:395-408) on identical
+// data and reaches the identical decision; the accepted candidate then travels from its owner to the others (all-reduce of its bits).
+#define CKN(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess){ h->err = std::string(#call) + ": " + (h->nccl.GetErrorString ? h->nccl.GetErrorString(r_) : "NCCL error"); return PDDP_E_CUDA; } } while (0)
+static int run_iterations_alpha_sharded(pddp_handle h){
+    DevState &S = h->S; cudaStream_t st = h->stream; int rc;
+    const size_t per = (size_t)S.N*(2*S.n + S.m);
+    for (int it = 0; it < S.iter_cap; it++){
+        if ((rc = launch_bp(h, st, 0, S.B))){ return rc; }
+        if ((rc = launch_sweep(h, st, 0, S.B))){ return rc; }
+        if ((rc = launch_sim(h, st, 0, S.B))){ return rc; }
+        select_kernel<<<S.B, 32*S.a_cnt, h->smem_sel, st>>>(S, 2, 0); h->launches += 1; CK(cudaGetLastError());
+        CK(cudaEventRecord(h->xev[0], st));
+        CKN(h->nccl.AllGather(S.xchg_send, S.xchg_recv, (size_t)S.B*S.a_cnt*2, ncclFloat32, h->nccl.comm, st));
+        CK(cudaEventRecord(h->xev[1], st));
+        select_kernel<<<S.B, 32*S.A, h->smem_sel, st>>>(S, 3, 0); h->launches += 1; CK(cudaGetLastError());
+        ashard_pack_kernel<<<S.B, 256, 0, st>>>(S); h->launches += 1; CK(cudaGetLastError());
+        CK(cudaEventRecord(h->xev[2], st));
+        CKN(h->nccl.AllReduce(S.acc_buf, S.acc_buf, (size_t)S.B*per, ncclInt32, ncclSum, h->nccl.comm, st));
+        CK(cudaEventRecord(h->xev[3], st));
+        ashard_unpack_kernel<<<S.B, 256, 0, st>>>(S); h->launches += 1; CK(cudaGetLastError());
+        if ((rc = launch_nis(h, st, 0, S.B))){ return rc; }
+        if (it == S.iter_cap - 1 || (it % 8) == 7){
+            // exchange time of this iteration (sampled: reading events synchronises) and, with TOL_COST > 0, the convergence poll
+            CK(cudaMemcpyAsync(h->h_nactive, S.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            float a = 0, b = 0; cudaEventElapsedTime(&a, h->xev[0], h->xev[1]); cudaEventElapsedTime(&b, h->xev[2], h->xev[3]);
+            h->xchg_ms += a + b; h->xchg_calls += 1;
+            if (h->cfg.tol_cost > 0.0f && *h->h_nactive == 0){ break; }
+        }
+    }
+    return 0;
+}
+
 static int run_iterations(pddp_handle h, double *times_ms, int groups){
     DevState &S = h->S;
+    if (h->nccl.comm){
+        if (times_ms){ times_ms[1] = times_ms[2] = times_ms[3] = times_ms[4] = 0.0; }
+        return run_iterations_alpha_sharded(h);
+    }
     const bool timing = times_ms != nullptr && groups == 1;
     if (!timing && h->use_graphs){
         if (times_ms){ times_ms[1] = times_ms[2] = times_ms[3] = times_ms[4] = 0.0; }
@@ -493,6 +546,8 @@ extern "C" int pddp_solve_device(pddp_handle h, const float *d_x0, const float *
     DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m; int rc;
     CK(cudaSetDevice(h->cfg.device));
     h->launches = 0; h->graph_launches = 0;
+    if (h->nccl.comm && (h->next_rollout || !h->next_clear)){ h->err = "step-size sharding: cold starts only (rollout = 0, clear = 1)"; return PDDP_E_INVALID; }
+    h->xchg_ms = 0; h->xchg_calls = 0;
     CK(cudaEventRecord(h->ev[0], h->stream));
     if ((rc = launch_reset(h, ignoreFirstDefectFlag, h->next_clear))){ return rc; }
     CK(cudaMemcpyAsync(S.xp, d_x0, (size_t)B*N*n*4, cudaMemcpyDeviceToDevice, h->stream));
@@ -621,6 +676,7 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
                              int ignoreFirstDefectFlag, float *x, float *u, float *KT, float *Jout, int *alphaOut, int *iters_out, int *last_successful_solve){
     if (!h){ return PDDP_E_INVALID; }
     if (!h->mpc_ready){ h->err = "pddp_mpc_init first"; return PDDP_E_INVALID; }
+    if (h->nccl.comm){ h->err = "step-size sharding: plain solves only"; return PDDP_E_INVALID; }
     if (!xActual || !xGoal || !shiftAmount || !x || !u || !KT){ h->err = "null input"; return PDDP_E_INVALID; }
     DevState &S = h->S; const int B = S.B, N = S.N, n = S.n, m = S.m, L = S.max_iter + 1; int rc;
     if (max_iter < 1 || max_iter > S.max_iter){ h->err = "max_iter of the step must be in [1, config max_iter]"; return PDDP_E_INVALID; }
@@ -812,6 +868,49 @@ extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
     cudaFree(d);
     return e == cudaSuccess ? 0 : PDDP_E_CUDA;
 }
+// ---------------------------------------------------------------------------------------------------- step-size sharding over GPUs
+extern "C" int pddp_alpha_shard_unique_id(void *id128){
+    if (!id128){ return PDDP_E_INVALID; }
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib){ g_plant_error = std::string("dlopen libnccl.so.2: ") + dlerror(); return PDDP_E_INVALID; }
+    auto fn = reinterpret_cast<ncclResult_t (*)(ncclUniqueId*)>(dlsym(lib, "ncclGetUniqueId"));
+    if (!fn){ return PDDP_E_INVALID; }
+    static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id");
+    return fn(static_cast<ncclUniqueId*>(id128)) == ncclSuccess ? 0 : PDDP_E_CUDA;
+}
+extern "C" int pddp_alpha_shard_init(pddp_handle h, int rank, int nranks, const void *id128){
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks){ return PDDP_E_INVALID; }
+    DevState &S = h->S;
+    if (h->ops){ h->err = "step-size sharding is built for the Kuka kernels (PLANT 4)"; return PDDP_E_INVALID; }
+    if (S.ee){ h->err = "step-size sharding: joint-space cost only"; return PDDP_E_INVALID; }
+    if (S.A % nranks){ h->err = "n_alpha must be a multiple of the number of ranks"; return PDDP_E_INVALID; }
+    CK(cudaSetDevice(h->cfg.device));
+    auto &nc = h->nccl;
+    nc.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!nc.lib){ h->err = std::string("dlopen libnccl.so.2: ") + dlerror(); return PDDP_E_INVALID; }
+    #define SYM(field, name) nc.field = reinterpret_cast<decltype(nc.field)>(dlsym(nc.lib, name)); if (!nc.field){ h->err = std::string("libnccl lacks ") + name; return PDDP_E_INVALID; }
+    SYM(CommInitRank, "ncclCommInitRank") SYM(AllGather, "ncclAllGather") SYM(AllReduce, "ncclAllReduce") SYM(CommDestroy, "ncclCommDestroy") SYM(GetErrorString, "ncclGetErrorString")
+    #undef SYM
+    ncclUniqueId id; std::memcpy(&id, id128, sizeof(id));
+    CKN(nc.CommInitRank(&nc.comm, nranks, id, rank));
+    nc.rank = rank; nc.nranks = nranks;
+    S.a_cnt = S.A / nranks; S.a_first = rank*S.a_cnt;
+    const size_t per = (size_t)S.N*(2*S.n + S.m);
+    void *p = nullptr;
+    CK(cudaMalloc(&p, (size_t)S.B*S.a_cnt*2*4)); S.xchg_send = (float*)p; h->allocs.push_back(p);
+    CK(cudaMalloc(&p, (size_t)S.B*S.A*2*4)); S.xchg_recv = (float*)p; h->allocs.push_back(p);
+    CK(cudaMalloc(&p, (size_t)S.B*per*4)); S.acc_buf = (int*)p; h->allocs.push_back(p);
+    for (auto &e : h->xev){ CK(cudaEventCreate(&e)); }
+    return 0;
+}
+extern "C" int pddp_alpha_shard_stats(pddp_handle h, double *exchange_us_per_iteration, int *a_first, int *a_cnt){
+    if (!h){ return PDDP_E_INVALID; }
+    if (exchange_us_per_iteration){ *exchange_us_per_iteration = h->xchg_calls ? 1000.0*h->xchg_ms/h->xchg_calls : 0.0; }
+    if (a_first){ *a_first = h->S.a_first; } if (a_cnt){ *a_cnt = h->S.a_cnt; }
+    return 0;
+}
+
+extern "C" int pddp_set_bp_shape(pddp_handle h, int shape){ if (!h || shape < 0 || shape > 2){ return PDDP_E_INVALID; } h->bp_shape = shape; return 0; }
 extern "C" long pddp_last_launch_count(pddp_handle h){ return h ? h->launches : 0; }
 extern "C" long pddp_last_graph_launch_count(pddp_handle h){ return h ? h->graph_launches : 0; }
 extern "C" int pddp_set_graphs(pddp_handle h, int on, int iterations_per_graph){
