@@ -287,6 +287,27 @@ def main():
         strong = {"global_batch": STRONG_BATCH, "batch_per_gpu": sb, "n_gpus": world, "value": it2 / (ms2 / 1000.0), "unit": UNIT, "steps": nst,
                   "ms_per_step": ms2 / nst, "scaling": "strong", "note": "the 1-GPU run of this leg is the denominator of the N-GPU speed-up"}
         s2.freeMemory_GPU(); del e_x0, e_u0, e_xg, e_x, e_u, e_J, e_a, e_it
+    # the other multi-GPU mode (north_star): ONE problem, its line search's step sizes sharded over the ranks, one NCCL exchange at selection
+    # (libpddp's own communicator: pddp_alpha_shard_init).  Reported as latency per iteration next to the collective's share.
+    ashard = None
+    if world > 1 and not BENCH_EE and N_ALPHA % world == 0 and os.environ.get("PDDP_BENCH_ALPHA_SHARD", "1") != "0":
+        uid = [pddp.alpha_shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=dev)
+        s3 = pddp.Solver(pddp.default_config_kuka(N, 1, device=local_rank, tol_cost=0.0, max_iter=50))
+        s3.alpha_shard_init(rank, world, uid[0])
+        a1, b1, g1 = pddp.make_inputs_kuka(N, 1, seed0=0)
+        s3.runiLQR_GPU(a1, b1, g1); barrier()
+        t0 = time.time(); reps = 5
+        for _ in range(reps):
+            o3 = s3.runiLQR_GPU(a1, b1, g1)
+        barrier()
+        t3 = torch.tensor([(time.time() - t0) / reps, s3.alpha_shard_stats()["exchange_us_per_iteration"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        ashard = {"workload": "1 problem, Kuka N=128, alpha=16 split over the ranks, 50 iterations, host buffers", "n_gpus": world, "step_sizes_per_gpu": N_ALPHA // world,
+                  "ms_per_iteration": 1000.0 * t3[0].item() / 50, "nccl_exchange_us_per_iteration": t3[1].item(),
+                  "collectives_per_iteration": "1 ncclAllGather of 2*alpha floats (selection) + 1 ncclAllReduce of the accepted candidate (4 N (2n+m) B)",
+                  "final_cost": float(o3["Jout"][0, 50])}
+        s3.freeMemory_GPU()
     h2d = x0.nbytes + u0.nbytes + xg.nbytes
     d2h = o["x"].nbytes + o["u"].nbytes + o["Jout"].nbytes + o["alphaOut"].nbytes + o["iters"].nbytes
     stats = torch.tensor([dev_ms, e2e_s, float(iters_rank), float(e2e_iters), phase[3]], dtype=torch.float64, device=dev)
@@ -339,6 +360,8 @@ def main():
                                                  "current_source_sha1": cur, "stale": tr.get("kernel_source_sha1") != cur}
         if strong is not None:
             out["strong"] = strong
+        if ashard is not None:
+            out["alpha_sharded"] = ashard
         if world == 1:
             out["cpu_baseline"] = cpu_baseline()
             rg = ref_gpu_run()
