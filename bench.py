@@ -358,6 +358,24 @@ def main():
             out["roofline"]["traffic"] = tr.get("dram_bytes_per_launch")
             out["roofline"]["traffic_source"] = {"file": "profiles/bp_traffic.json", "captured_from_source_sha1": tr.get("kernel_source_sha1"),
                                                  "current_source_sha1": cur, "stale": tr.get("kernel_source_sha1") != cur}
+        # the same kernel where it saturates: the backward pass alone over 2048 problems (8192 chains: the warp-chain shape), timed by the
+        # library's CUDA events through the phase-level entry point
+        if world == 1 and os.environ.get("PDDP_BENCH_LARGE", "1") != "0":
+            LB = 2048
+            s4 = pddp.Solver(pddp.default_config_kuka(N, LB, device=local_rank, tol_cost=0.0, max_iter=3))
+            a4, b4, g4 = pddp.make_inputs_kuka(N, 64, seed0=0)
+            s4.load_init(np.tile(a4, (LB // 64, 1, 1)), np.tile(b4, (LB // 64, 1, 1)), np.tile(g4, (LB // 64, 1)))
+            ts = []
+            for it in range(7):
+                flush.fill_(1); torch.cuda.synchronize()
+                s4.backwardPassGPU(); ts.append(s4.last_phase_ms()[0])
+                if it < 2:
+                    s4.forwardSweep(); s4.forwardSimGPU(); s4.nextIterationSetupGPU()
+            t4 = float(np.median(ts[2:])) * 1e-3
+            out["roofline_large_batch"] = {"kernel": "bp_warp_kernel (warp chains, chosen by launch size)", "bound": "hbm", "problems_per_launch": LB,
+                                           "achieved": LB * BP_BYTES_PER_PROBLEM / t4 / 1e9, "peak": peak, "unit": "GB/s",
+                                           "frac": LB * BP_BYTES_PER_PROBLEM / t4 / 1e9 / peak, "avg_launch_us": t4 * 1e6, "peak_source": peak_src}
+            s4.freeMemory_GPU()
         if strong is not None:
             out["strong"] = strong
         if ashard is not None:

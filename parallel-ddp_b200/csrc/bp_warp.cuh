@@ -23,25 +23,30 @@ namespace pddp {
 
 constexpr int BPW_WARPS = 4;             // chains per CTA
 constexpr int BPW_RS = 12;               // row stride of the 7-vectors (Hux, Huu, Hinv, K, T): two 16-byte loads per row
+constexpr int BPW_P = 20;                // row pitch of P, P + rho I and AB2: a 14-vector is four 16-byte loads (two per half); 20 words put the
+                                         // rows r, r+1, ... r+7 on disjoint bank quads, so lanes that read consecutive rows do not conflict
 struct __align__(16) BpWarpSmem {
     float AB[2][AB_STRIDE], Hc[2][H_STRIDE], gc[2][G_STRIDE];      // ring of knot inputs; H is assembled in place in Hc
-    float P[196], Pr[196];                                         // P and P + rho on the diagonal (the operand of the u-rows of AB'(.))
-    float AB2[296];                                                // AB2[kx*14 + ky]; T[kx*BPW_RS + j] lives here from stage D on
+    float P[14*BPW_P], Pr[14*BPW_P];                               // P[ky][kx] and P + rho on the diagonal (the operand of the u-rows of AB'(.))
+    float AB2[21*BPW_P];                                           // AB2[kx][ky]; T[kx*BPW_RS + j] lives here from stage D on
     float Hux[14*BPW_RS], K[14*BPW_RS], Huu[7*BPW_RS], Hinv[7*BPW_RS];
     float g[24], p[16], dx[16], du[8], pad[8];
     unsigned long long full[2];
 };
 static_assert(sizeof(BpWarpSmem) % 16 == 0, "warp workspaces must keep 16-byte alignment");
 
-__device__ __forceinline__ void bpw_ld14(float (&x)[14], const float *p){
-    const float2 *q = reinterpret_cast<const float2*>(p);
-    #pragma unroll
-    for (int i = 0; i < 7; i++){ const float2 v = q[i]; x[2*i] = v.x; x[2*i+1] = v.y; }
-}
 __device__ __forceinline__ void bpw_ld8(float (&x)[8], const float *p){
     const float4 *q = reinterpret_cast<const float4*>(p);
     const float4 a = q[0], b = q[1];
     x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+// eight (HALF = 0: entries 0..7) or six (HALF = 1: entries 8..13) floats of a 14-vector stored with 8-byte alignment (the rows of AB)
+template <int HALF>
+__device__ __forceinline__ void bpw_ldh64(float (&x)[8], const float *p){
+    const float2 *q = reinterpret_cast<const float2*>(p + 8*HALF);
+    #pragma unroll
+    for (int i = 0; i < (HALF ? 3 : 4); i++){ const float2 v = q[i]; x[2*i] = v.x; x[2*i+1] = v.y; }
+    if (HALF){ x[6] = 0.f; x[7] = 0.f; }
 }
 template <int K, int KP>
 __device__ __forceinline__ float bpw_dot(const float (&x)[KP], const float (&y)[KP]){
@@ -52,16 +57,10 @@ __device__ __forceinline__ float bpw_dot(const float (&x)[KP], const float (&y)[
 }
 
 #ifndef PDDP_BPW_MINCTA
-#define PDDP_BPW_MINCTA 5
+#define PDDP_BPW_MINCTA 4
 #endif
-#ifndef PDDP_BPW_UNROLL
-#define PDDP_BPW_UNROLL 1
-#endif
-#define BPW_PRAGMA2(x) _Pragma(#x)
-#define BPW_PRAGMA(x) BPW_PRAGMA2(x)
-#define BPW_UNROLL BPW_PRAGMA(unroll PDDP_BPW_UNROLL)
 __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(DevState S, int b0, int nchains){
-    constexpr int n = 14, m = 7, nm = 21, oB = n*n;
+    constexpr int n = 14, m = 7, nm = 21, oB = n*n, PP = BPW_P;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int chain = blockIdx.x*BPW_WARPS + w;
@@ -97,25 +96,36 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
         const size_t kN = bN + N - 1;
         for (int e = l; e < n*n; e += 32){
             const int kx = e % n, ky = e / n; const float v = MUL(1.0f, S.H[kN*H_STRIDE + kx + nm*ky]);
-            s.P[e] = v; s.Pr[e] = (kx == ky) ? ADD(v, rho) : v; gPcur[(kN-1)*n*n + e] = v;
+            s.P[ky*PP + kx] = v; s.Pr[ky*PP + kx] = (kx == ky) ? ADD(v, rho) : v; gPcur[(kN-1)*n*n + e] = v;
         }
         if (l < n){ const float v = MUL(1.0f, S.g[kN*G_STRIDE + l]); s.p[l] = v; gpcur[(kN-1)*n + l] = v; }
     } else {
         // other blocks: the previous iteration's P, p at the block boundary, p shifted to the new linearisation point (:369,376)
         const float *gPp = S.Pbuf[cur^1] + (bN + ks)*n*n;
-        for (int e = l; e < n*n; e += 32){ const float v = gPp[e]; s.P[e] = v; s.Pr[e] = (e % n == e / n) ? ADD(v, rho) : v; }
+        for (int e = l; e < n*n; e += 32){ const int kx = e % n, ky = e / n; const float v = gPp[e]; s.P[ky*PP + kx] = v; s.Pr[ky*PP + kx] = (kx == ky) ? ADD(v, rho) : v; }
         if (l < n){ s.dx[l] = SUB(S.xp[(bN + ks + 1)*n + l], S.xp2[(bN + ks + 1)*n + l]); }
         __syncwarp();
         if (l < n){
             float val = 0.f;
             #pragma unroll
-            for (int j = 0; j < n; j++){ val = FMA(s.P[l + n*j], s.dx[j], val); }
+            for (int j = 0; j < n; j++){ val = FMA(s.P[l + PP*j], s.dx[j], val); }
             s.p[l] = FMA(1.0f, val, S.pbuf[cur^1][(bN + ks)*n + l]);
         }
     }
     __syncwarp();
     float dJ0 = 0.f, dJ1 = 0.f;               // lanes 0..6: running sums of du*gu and du*(Huu du) (bpHelpers.cuh:327-328)
-    const int hl = min(l & 7, 6), hg = l >> 3;                      // Huu: lane = l' + 8*(column pair)
+    // ---- tile coordinates (fixed per lane)
+    // stage A: (up to 3 columns kx of AB, not straddling the x / u boundary) x (rows ky = q, q+4, q+8, q+12 of P): 8 x 4 = 32 tiles.
+    // Row groups are interleaved: at any one load the four groups read four CONSECUTIVE rows (disjoint banks), never rows 4 apart
+    const int a_g = l & 7, a_q = l >> 3;
+    const int a_kx0 = a_g < 5 ? 3*a_g : n + 3*(a_g - 5), a_cnt = (a_g == 4) ? 2 : (a_g == 7 ? 1 : 3);
+    const int a_kx1 = a_cnt > 1 ? a_kx0 + 1 : a_kx0, a_kx2 = a_cnt > 2 ? a_kx0 + 2 : a_kx0;
+    const int a_ky0 = a_q, a_ky1 = a_q + 4, a_ky2 = a_q + 8, a_ky3 = a_q < 2 ? a_q + 12 : a_q;                  // rows 12, 13 exist for q = 0, 1 only
+    // stage B: (rows r = g, g+6, g+12, g+18 of AB2) x (5 columns kx of AB): 6 x 5 = 30 tiles of the 21 x 21 matrix H (rows interleaved as above)
+    const int h_rg = min(l / 5, 5), h_cg = l % 5;
+    const int h_r0 = h_rg, h_rc = h_rg < 3 ? 4 : 3, h_k0 = 5*h_cg, h_kc = h_cg < 4 ? 5 : 1;
+    // stage E: (2 rows kx) x (4 rows ky) of P: 7 x 4 = 28 tiles
+    const int e_kx0 = 2*(l % 7), e_q = min(l / 7, 3), e_ky0 = 4*e_q, e_kc = e_q < 3 ? 4 : 2;
     #pragma unroll 1
     for (int iter = iterCount, i = 0; iter >= 0; iter--, ks--, i++){
         const int slot = i & 1;
@@ -125,95 +135,96 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
         const size_t kk = bN + ks;
         const bool boundary = S.M > 1 && iter == NBB - 1;           // block-local defect-boundary test of the reference (bpHelpers.cuh:73)
         // ---- stage A: AB2 = AB'(P + rho I[u rows]); p += P d on the boundary
-        BPW_UNROLL
-        for (int tile = l; tile < 56; tile += 32){
-            const int a_g = tile & 7, a_kp = tile >> 3;
-            const int a_kx0 = a_g < 5 ? 3*a_g : n + 3*(a_g - 5), a_cnt = (a_g == 4) ? 2 : (a_g == 7 ? 1 : 3);
-            const int a_kx1 = a_cnt > 1 ? a_kx0 + 1 : a_kx0, a_kx2 = a_cnt > 2 ? a_kx0 + 2 : a_kx0;
-            float x0[14], x1[14], x2[14], y0[14], y1[14];
+        {
             const float *Pq = (a_kx0 >= n) ? s.Pr : s.P;
-            bpw_ld14(x0, sAB + a_kx0*n); bpw_ld14(x1, sAB + a_kx1*n); bpw_ld14(x2, sAB + a_kx2*n);
-            bpw_ld14(y0, Pq + (2*a_kp)*n); bpw_ld14(y1, Pq + (2*a_kp+1)*n);
-            float v00 = 0.f, v01 = 0.f, v10 = 0.f, v11 = 0.f, v20 = 0.f, v21 = 0.f;
+            float v[3][4];
             #pragma unroll
-            for (int j = 0; j < n; j++){
-                v00 = FMA(x0[j], y0[j], v00); v01 = FMA(x0[j], y1[j], v01);
-                v10 = FMA(x1[j], y0[j], v10); v11 = FMA(x1[j], y1[j], v11);
-                v20 = FMA(x2[j], y0[j], v20); v21 = FMA(x2[j], y1[j], v21);
+            for (int c = 0; c < 3; c++){
+                #pragma unroll
+                for (int r = 0; r < 4; r++){ v[c][r] = 0.f; }
             }
-            *reinterpret_cast<float2*>(&s.AB2[a_kx0*n + 2*a_kp]) = make_float2(v00, v01);
-            if (a_cnt > 1){ *reinterpret_cast<float2*>(&s.AB2[a_kx1*n + 2*a_kp]) = make_float2(v10, v11); }
-            if (a_cnt > 2){ *reinterpret_cast<float2*>(&s.AB2[a_kx2*n + 2*a_kp]) = make_float2(v20, v21); }
+            #define BPW_A_HALF(HALF) { \
+                float x0[8], x1[8], x2[8], y0[8], y1[8], y2[8], y3[8]; \
+                bpw_ldh64<HALF>(x0, sAB + a_kx0*n); bpw_ldh64<HALF>(x1, sAB + a_kx1*n); bpw_ldh64<HALF>(x2, sAB + a_kx2*n); \
+                bpw_ld8(y0, Pq + a_ky0*PP + 8*HALF); bpw_ld8(y1, Pq + a_ky1*PP + 8*HALF); bpw_ld8(y2, Pq + a_ky2*PP + 8*HALF); bpw_ld8(y3, Pq + a_ky3*PP + 8*HALF); \
+                _Pragma("unroll") \
+                for (int j = 0; j < (HALF ? 6 : 8); j++){ \
+                    v[0][0] = FMA(x0[j], y0[j], v[0][0]); v[0][1] = FMA(x0[j], y1[j], v[0][1]); v[0][2] = FMA(x0[j], y2[j], v[0][2]); v[0][3] = FMA(x0[j], y3[j], v[0][3]); \
+                    v[1][0] = FMA(x1[j], y0[j], v[1][0]); v[1][1] = FMA(x1[j], y1[j], v[1][1]); v[1][2] = FMA(x1[j], y2[j], v[1][2]); v[1][3] = FMA(x1[j], y3[j], v[1][3]); \
+                    v[2][0] = FMA(x2[j], y0[j], v[2][0]); v[2][1] = FMA(x2[j], y1[j], v[2][1]); v[2][2] = FMA(x2[j], y2[j], v[2][2]); v[2][3] = FMA(x2[j], y3[j], v[2][3]); \
+                } }
+            BPW_A_HALF(0) BPW_A_HALF(1)
+            #undef BPW_A_HALF
+            #pragma unroll
+            for (int c = 0; c < 3; c++){
+                if (c < a_cnt){
+                    float *o = &s.AB2[(a_kx0 + c)*PP];
+                    o[a_ky0] = v[c][0]; o[a_ky1] = v[c][1]; o[a_ky2] = v[c][2];
+                    if (a_q < 2){ o[a_ky3] = v[c][3]; }
+                }
+            }
         }
         if (l < n){
             float val = 0.f;
             if (boundary){
                 const float *gd = S.dp + kk*n;
                 #pragma unroll
-                for (int j = 0; j < n; j++){ val = FMA(gd[j], s.P[l + n*j], val); }
+                for (int j = 0; j < n; j++){ val = FMA(gd[j], s.P[l + PP*j], val); }
             }
             s.p[l] = ADD(s.p[l], val);
         }
         __syncwarp();
         // ---- stage B: H = (AB2 AB)' + H_cost (in place in the ring slot), g = AB'p + g_cost
-        // region 1 (rows ky < n, all columns): tile = 2 rows of AB2 x 3 columns of AB
-        BPW_UNROLL
-        for (int tile = l; tile < 49; tile += 32){
-            const int kx0 = 3*(tile % 7), r0 = 2*(tile / 7);
-            float x0[14], x1[14], x2[14], y0[14], y1[14];
-            bpw_ld14(x0, sAB + kx0*n); bpw_ld14(x1, sAB + (kx0+1)*n); bpw_ld14(x2, sAB + (kx0+2)*n);
-            bpw_ld14(y0, s.AB2 + r0*n); bpw_ld14(y1, s.AB2 + (r0+1)*n);
-            float q[6];
+        if (l < 30){
+            float v[4][5];
             #pragma unroll
-            for (int c = 0; c < 3; c++){ q[c] = sH[kx0 + c + nm*r0]; q[3+c] = sH[kx0 + c + nm*(r0+1)]; }
-            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            #pragma unroll
-            for (int j = 0; j < n; j++){
-                v[0] = FMA(y0[j], x0[j], v[0]); v[1] = FMA(y0[j], x1[j], v[1]); v[2] = FMA(y0[j], x2[j], v[2]);
-                v[3] = FMA(y1[j], x0[j], v[3]); v[4] = FMA(y1[j], x1[j], v[4]); v[5] = FMA(y1[j], x2[j], v[5]);
+            for (int r = 0; r < 4; r++){
+                #pragma unroll
+                for (int c = 0; c < 5; c++){ v[r][c] = 0.f; }
             }
+            const int r1 = h_r0 + 6, r2 = h_r0 + 12, r3 = h_rc > 3 ? h_r0 + 18 : h_r0;
+            const int k1 = h_kc > 1 ? h_k0 + 1 : h_k0, k2 = h_kc > 1 ? h_k0 + 2 : h_k0, k3 = h_kc > 1 ? h_k0 + 3 : h_k0, k4 = h_kc > 1 ? h_k0 + 4 : h_k0;
+            #define BPW_H_HALF(HALF) { \
+                float y0[8], y1[8], y2[8], y3[8], x0[8], x1[8], x2[8], x3[8], x4[8]; \
+                bpw_ld8(y0, s.AB2 + h_r0*PP + 8*HALF); bpw_ld8(y1, s.AB2 + r1*PP + 8*HALF); bpw_ld8(y2, s.AB2 + r2*PP + 8*HALF); bpw_ld8(y3, s.AB2 + r3*PP + 8*HALF); \
+                bpw_ldh64<HALF>(x0, sAB + h_k0*n); bpw_ldh64<HALF>(x1, sAB + k1*n); bpw_ldh64<HALF>(x2, sAB + k2*n); bpw_ldh64<HALF>(x3, sAB + k3*n); bpw_ldh64<HALF>(x4, sAB + k4*n); \
+                _Pragma("unroll") \
+                for (int j = 0; j < (HALF ? 6 : 8); j++){ \
+                    v[0][0] = FMA(y0[j], x0[j], v[0][0]); v[0][1] = FMA(y0[j], x1[j], v[0][1]); v[0][2] = FMA(y0[j], x2[j], v[0][2]); v[0][3] = FMA(y0[j], x3[j], v[0][3]); v[0][4] = FMA(y0[j], x4[j], v[0][4]); \
+                    v[1][0] = FMA(y1[j], x0[j], v[1][0]); v[1][1] = FMA(y1[j], x1[j], v[1][1]); v[1][2] = FMA(y1[j], x2[j], v[1][2]); v[1][3] = FMA(y1[j], x3[j], v[1][3]); v[1][4] = FMA(y1[j], x4[j], v[1][4]); \
+                    v[2][0] = FMA(y2[j], x0[j], v[2][0]); v[2][1] = FMA(y2[j], x1[j], v[2][1]); v[2][2] = FMA(y2[j], x2[j], v[2][2]); v[2][3] = FMA(y2[j], x3[j], v[2][3]); v[2][4] = FMA(y2[j], x4[j], v[2][4]); \
+                    v[3][0] = FMA(y3[j], x0[j], v[3][0]); v[3][1] = FMA(y3[j], x1[j], v[3][1]); v[3][2] = FMA(y3[j], x2[j], v[3][2]); v[3][3] = FMA(y3[j], x3[j], v[3][3]); v[3][4] = FMA(y3[j], x4[j], v[3][4]); \
+                } }
+            BPW_H_HALF(0) BPW_H_HALF(1)
+            #undef BPW_H_HALF
             #pragma unroll
-            for (int c = 0; c < 3; c++){
-                const float h0 = FMA(1.0f, v[c], MUL(1.0f, q[c])), h1 = FMA(1.0f, v[3+c], MUL(1.0f, q[3+c]));
-                sH[kx0 + c + nm*r0] = h0; sH[kx0 + c + nm*(r0+1)] = h1;
-                if (kx0 + c >= n){ s.Hux[r0*BPW_RS + kx0 + c - n] = h0; s.Hux[(r0+1)*BPW_RS + kx0 + c - n] = h1; }
+            for (int r = 0; r < 4; r++){
+                if (r < h_rc){
+                    const int rr = h_r0 + 6*r;
+                    #pragma unroll
+                    for (int c = 0; c < 5; c++){
+                        if (c < h_kc){
+                            const int kx = h_k0 + c;
+                            const float h = FMA(1.0f, v[r][c], MUL(1.0f, sH[kx + nm*rr]));
+                            sH[kx + nm*rr] = h;
+                            if (kx >= n){ if (rr < n){ s.Hux[rr*BPW_RS + kx - n] = h; } else { s.Huu[(rr - n)*BPW_RS + kx - n] = h; } }
+                        }
+                    }
+                }
             }
-        }
-        // region 2 (rows ky >= n, columns < n): tile = 1 row of AB2 x 2 columns of AB
-        BPW_UNROLL
-        for (int tile = l; tile < 49; tile += 32){
-            const int kxp = tile % 7, ky = n + tile / 7;
-            float y[14], x0[14], x1[14];
-            bpw_ld14(y, s.AB2 + ky*n); bpw_ld14(x0, sAB + (2*kxp)*n); bpw_ld14(x1, sAB + (2*kxp+1)*n);
-            const float q0 = sH[2*kxp + nm*ky], q1 = sH[2*kxp + 1 + nm*ky];
-            float v0 = 0.f, v1 = 0.f;
-            #pragma unroll
-            for (int j = 0; j < n; j++){ v0 = FMA(y[j], x0[j], v0); v1 = FMA(y[j], x1[j], v1); }
-            sH[2*kxp + nm*ky] = FMA(1.0f, v0, MUL(1.0f, q0)); sH[2*kxp + 1 + nm*ky] = FMA(1.0f, v1, MUL(1.0f, q1));
         }
         if (l < nm){
-            float x[14], y[14];
-            bpw_ld14(x, s.p); bpw_ld14(y, sAB + l*n);
-            s.g[l] = FMA(1.0f, bpw_dot<n>(x, y), MUL(1.0f, bg[l]));
-        }
-        // Huu: lane l' + 8*q computes Huu(l', 2q) and Huu(l', 2q+1); the rows are then gathered on lanes 0..6 for the elimination
-        {
-            float x[14], y0[14], y1[14];
-            const int c0 = min(2*hg, 6), c1 = min(2*hg + 1, 6);
-            bpw_ld14(x, sAB + (n + hl)*n); bpw_ld14(y0, s.AB2 + (n + c0)*n); bpw_ld14(y1, s.AB2 + (n + c1)*n);
-            const float q0 = sH[(n + hl) + nm*(n + c0)], q1 = sH[(n + hl) + nm*(n + c1)];
-            float v0 = 0.f, v1 = 0.f;
+            float val = 0.f;
             #pragma unroll
-            for (int j = 0; j < n; j++){ v0 = FMA(y0[j], x[j], v0); v1 = FMA(y1[j], x[j], v1); }
-            const float h0 = FMA(1.0f, v0, MUL(1.0f, q0)), h1 = FMA(1.0f, v1, MUL(1.0f, q1));
-            __syncwarp();                         // every lane has read its Hc operands of the u x u block before it is overwritten
-            if ((l & 7) < 7){
-                sH[(n + hl) + nm*(n + c0)] = h0; s.Huu[c0*BPW_RS + hl] = h0;
-                if (2*hg + 1 < m){ sH[(n + hl) + nm*(n + c1)] = h1; s.Huu[c1*BPW_RS + hl] = h1; }
-            }
+            for (int j = 0; j < n; j++){ val = FMA(s.p[j], sAB[l*n + j], val); }
+            s.g[l] = FMA(1.0f, val, MUL(1.0f, bg[l]));
+        }
+        __syncwarp();
+        // Huu^-1: row l of [Huu | I] on lane l < 7, 7 x 7 Gauss-Jordan by shuffles
+        {
             float a[2*m];
             #pragma unroll
-            for (int c = 0; c < m; c++){ a[c] = MUL(1.0f, __shfl_sync(FULL, (c & 1) ? h1 : h0, (l & 7) + 8*(c >> 1))); a[m + c] = (l == c) ? 1.f : 0.f; }
+            for (int c = 0; c < m; c++){ a[c] = MUL(1.0f, s.Huu[c*BPW_RS + min(l, m - 1)]); a[m + c] = (l == c) ? 1.f : 0.f; }
             gauss_jordan_rows<m>(a, l);
             if (l < m){
                 *reinterpret_cast<float4*>(&s.Hinv[l*BPW_RS]) = make_float4(a[m], a[m+1], a[m+2], a[m+3]);
@@ -222,7 +233,7 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
         }
         __syncwarp();
         // ---- stage C: K = Huu^-1 Hux, du = Huu^-1 gu
-        BPW_UNROLL
+        #pragma unroll
         for (int e = l; e < n*m; e += 32){
             const int c_kx = e % m, c_ky = e / m;
             float hi[8], hx[8];
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
         const bool do_ctg = (iter != 0 || block != 0);
         float *sT = s.AB2;
         if (do_ctg){
-            BPW_UNROLL
+            #pragma unroll
             for (int e = l; e < n*m; e += 32){
                 const int d_kx = e % n, d_ky = e / n;
                 float k[8], h[8];
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
         __syncwarp();
         // ---- stage F (before E: it reads K, du and the knot's AB, none of which E changes): A - BK, B du, KT, du -> HBM
         if (S.M > 1){
-            BPW_UNROLL
+            #pragma unroll
             for (int e = l; e < 98; e += 32){
                 const int kx = e % n, kyp = e / n;
                 float bb[8], k0[8], k1[8];
@@ -279,9 +290,10 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
                 S.Bdu[kk*n + l] = val;
             }
         }
+        #pragma unroll
         for (int e = l; e < n*m; e += 32){ const int kx = e % n, ky = e / n; S.KT[kk*n*m + e] = s.K[kx*BPW_RS + ky]; }
         if (l < m){ S.du[kk*m + l] = s.du[l]; }
-        // ---- stage E: cost-to-go of the previous knot
+        // ---- stage E: cost-to-go of the previous knot: tile = rows kx0, kx0+1 of T and K x up to 4 rows ky of K and Hux
         if (do_ctg){
             float pv = 0.f;
             if (l < n){             // p first: it reads g and T, and nothing below changes them
@@ -292,28 +304,28 @@ __global__ void __launch_bounds__(32*BPW_WARPS, PDDP_BPW_MINCTA) bp_warp_kernel(
                 for (int j = 0; j < m; j++){ val = ADD(val, FMA(s.du[j], a[j], -MUL(k2[j], s.g[n + j]))); }
                 pv = ADD(s.g[l], val);
             }
-            BPW_UNROLL
-            for (int tile = l; tile < 49; tile += 32){
-                const int kx0 = 2*(tile % 7), ky0 = 2*(tile / 7);
-                float a0[8], a1[8], kx_0[8], kx_1[8], ky_0[8], ky_1[8], h0[8], h1[8];
-                bpw_ld8(a0, sT + kx0*BPW_RS); bpw_ld8(a1, sT + (kx0+1)*BPW_RS); bpw_ld8(kx_0, s.K + kx0*BPW_RS); bpw_ld8(kx_1, s.K + (kx0+1)*BPW_RS);
-                bpw_ld8(ky_0, s.K + ky0*BPW_RS); bpw_ld8(ky_1, s.K + (ky0+1)*BPW_RS); bpw_ld8(h0, s.Hux + ky0*BPW_RS); bpw_ld8(h1, s.Hux + (ky0+1)*BPW_RS);
-                const float x00 = sH[kx0 + ky0*nm], x10 = sH[kx0 + 1 + ky0*nm], x01 = sH[kx0 + (ky0+1)*nm], x11 = sH[kx0 + 1 + (ky0+1)*nm];
-                float v00 = 0.f, v10 = 0.f, v01 = 0.f, v11 = 0.f;
-                #pragma unroll
-                for (int j = 0; j < m; j++){
-                    v00 = ADD(v00, FMA(a0[j], ky_0[j], -MUL(kx_0[j], h0[j]))); v10 = ADD(v10, FMA(a1[j], ky_0[j], -MUL(kx_1[j], h0[j])));
-                    v01 = ADD(v01, FMA(a0[j], ky_1[j], -MUL(kx_0[j], h1[j]))); v11 = ADD(v11, FMA(a1[j], ky_1[j], -MUL(kx_1[j], h1[j])));
-                }
-                const float p00 = ADD(x00, v00), p10 = ADD(x10, v10), p01 = ADD(x01, v01), p11 = ADD(x11, v11);
-                *reinterpret_cast<float2*>(&s.P[ky0*n + kx0]) = make_float2(p00, p10);
-                *reinterpret_cast<float2*>(&s.P[(ky0+1)*n + kx0]) = make_float2(p01, p11);
-                const bool dg = (kx0 == ky0);
-                *reinterpret_cast<float2*>(&s.Pr[ky0*n + kx0]) = make_float2(dg ? ADD(p00, rho) : p00, p10);
-                *reinterpret_cast<float2*>(&s.Pr[(ky0+1)*n + kx0]) = make_float2(p01, dg ? ADD(p11, rho) : p11);
+            if (l < 28){
+                float a0[8], a1[8], kx_0[8], kx_1[8];
+                bpw_ld8(a0, sT + e_kx0*BPW_RS); bpw_ld8(a1, sT + (e_kx0+1)*BPW_RS); bpw_ld8(kx_0, s.K + e_kx0*BPW_RS); bpw_ld8(kx_1, s.K + (e_kx0+1)*BPW_RS);
                 float *gP = gPcur + (kk-1)*n*n;
-                *reinterpret_cast<float2*>(&gP[ky0*n + kx0]) = make_float2(p00, p10);
-                *reinterpret_cast<float2*>(&gP[(ky0+1)*n + kx0]) = make_float2(p01, p11);
+                #pragma unroll
+                for (int r = 0; r < 4; r++){
+                    if (r < e_kc){
+                        const int ky = e_ky0 + r;
+                        float ky_[8], h_[8];
+                        bpw_ld8(ky_, s.K + ky*BPW_RS); bpw_ld8(h_, s.Hux + ky*BPW_RS);
+                        const float x0 = sH[e_kx0 + ky*nm], x1 = sH[e_kx0 + 1 + ky*nm];
+                        float v0 = 0.f, v1 = 0.f;
+                        #pragma unroll
+                        for (int j = 0; j < m; j++){
+                            v0 = ADD(v0, FMA(a0[j], ky_[j], -MUL(kx_0[j], h_[j]))); v1 = ADD(v1, FMA(a1[j], ky_[j], -MUL(kx_1[j], h_[j])));
+                        }
+                        const float p0 = ADD(x0, v0), p1 = ADD(x1, v1);
+                        *reinterpret_cast<float2*>(&s.P[ky*PP + e_kx0]) = make_float2(p0, p1);
+                        *reinterpret_cast<float2*>(&s.Pr[ky*PP + e_kx0]) = make_float2(e_kx0 == ky ? ADD(p0, rho) : p0, e_kx0 + 1 == ky ? ADD(p1, rho) : p1);
+                        *reinterpret_cast<float2*>(&gP[ky*n + e_kx0]) = make_float2(p0, p1);
+                    }
+                }
             }
             if (l < n){ s.p[l] = pv; gpcur[(kk-1)*n + l] = pv; }
         }
