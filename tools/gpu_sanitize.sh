@@ -28,6 +28,18 @@ e.mpc_init(x0, u0 * 0 + 0.01)
 for st in range(3):
     e.mpc_step(e.mpc_x[:, 0].copy(), xe, 0 if st == 0 else 2, 2, clear_vars=1 if st == 0 else 0)
 print("done ee", oe["iters"], oe2["iters"])
+# round 2: both backward-pass shapes, graph replay off / on, plug-in plants with all three integrators incl. the rho retry and a
+# receding-horizon step
+for shape in (1, 2):
+    s2 = pddp.Solver(pddp.default_config_kuka(N, B, max_iter=2)); s2.set_bp_shape(shape); s2.set_graphs(shape == 1, 2); s2.runiLQR_GPU(x0, u0, xg)
+for plant, integ, A in ((1, 3, 1), (2, 2, 8), (3, 3, 16), (3, 1, 4)):
+    c = pddp.default_config(plant, 32, B, n_alpha=A, integrator=integ, max_iter=3)
+    if plant == 2: c.R = -0.5          # forces the rho retry of the 1-D inverse
+    a0, b0, g0 = pddp.make_inputs(plant, 32, B, seed0=2)
+    sp = pddp.Solver(c); op = sp.runiLQR_GPU(a0, b0, g0)
+    sp.mpc_init(a0, b0); sp.mpc_step(a0[:, 1].copy(), g0, 1, 2)
+    sp.dynamics(a0[0, :3], b0[0, :3]); sp.integratorGradient(a0[0, :3], b0[0, :3]); sp.integrator(a0[0, :3], b0[0, :3]); sp.cost(a0[0, :3], b0[0, :3], g0[0], [0, 5, 31])
+    print("done plant", plant, integ, op["iters"])
 PY
 for tool in memcheck racecheck synccheck; do
   echo "== $tool"; timeout 500 compute-sanitizer --tool $tool python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done|Error|hazard" | head -8
