@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int b0){
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward simulation + per-knot cost + defects
-// grid = B*A/2 CTAs of 32*M threads: warp w simulates shooting interval w of TWO candidates (b, a) and (b, a+1), one per
+// grid = B*(A/2)*M CTAs of one warp: the warp simulates shooting interval w of TWO candidates (b, a) and (b, a+1), one per
 // half-warp (SIM_LANES = 16 lanes cooperate on one trajectory; both halves run the same instruction stream).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SIM_LANES = 16;
@@ -466,26 +466,28 @@ __device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const f
 // LANES = 32: one candidate per warp, the latency shape for small batches (fewer passes per phase: 13 % faster per knot when the
 // whole launch fits the machine with one warp per scheduler).  Same arithmetic either way; the host picks (launch_sim_any).
 template <bool EE, int LANES>
-__global__ void sim_kernel(DevState S, int b0, int n_cand, int a_first){
+__global__ void __launch_bounds__(32, 14) sim_kernel(DevState S, int b0, int n_cand, int a_first){
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int n = kuka::NX, m = kuka::NU, GPW = 32 / LANES;
-    float *sI = reinterpret_cast<float*>(smem_raw);            // 252
-    float *sTb = sI + 36*kuka::NB;                             // 252
+    float *sTb = reinterpret_cast<float*>(smem_raw);           // 252
     float *sxg = sTb + 36*kuka::NB;                            // 16
     SimGroupSmem *gsm = reinterpret_cast<SimGroupSmem*>(sxg + 16);
-    const int apb = (n_cand + GPW - 1) / GPW;                  // CTAs per problem (n_cand = A, or 1 for the initial rollout)
-    const int b = b0 + blockIdx.x / apb;
+    // one warp per CTA: the launch is a single wave bound by the shared-memory pipe of the fullest SM, and 2048 one-warp CTAs
+    // spread over 148 SMs as 13 or 14 warps each where 512 four-warp CTAs left 12 or 16
+    const int apb = (n_cand + GPW - 1) / GPW;                  // candidate groups per problem (n_cand = A, or 1 for the initial rollout)
+    const int w = blockIdx.x % S.M, pg = blockIdx.x / S.M;     // shooting interval; (problem, candidate group)
+    const int b = b0 + pg / apb;
     if (S.done[b]){ return; }
-    for (int i = threadIdx.x; i < 36*kuka::NB; i += blockDim.x){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
+    for (int i = threadIdx.x; i < 36*kuka::NB; i += 32){ sTb[i] = S.Tbody[i]; }
     if (threadIdx.x < n){ sxg[threadIdx.x] = S.xGoal[b*n + threadIdx.x]; }
-    __syncthreads();
-    const int w = threadIdx.x >> 5, grp = (threadIdx.x & 31) / LANES, l = threadIdx.x & (LANES-1);
-    if (w >= S.M){ return; }
-    int a = (blockIdx.x % apb)*GPW + grp;
+    __syncwarp();
+    const int grp = threadIdx.x / LANES, l = threadIdx.x & (LANES-1);
+    float Ib[36]; kuka::load_body_inertia<LANES>(S.I, Ib);     // lane 2 j + h: inertia of body j, in registers for the whole kernel
+    int a = (pg % apb)*GPW + grp;
     const bool live = a < n_cand;                              // odd count: the last half-warp replays the last candidate without storing
     if (!live){ a = n_cand - 1; }
     a += a_first;                                              // candidates a_first .. a_first + n_cand - 1 (step-size sharding)
-    SimGroupSmem &s = gsm[w*GPW + grp];
+    SimGroupSmem &s = gsm[grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
     // EE: every interval runs NBF steps -- the last one also evaluates knot N-1 for its pose cost (fpHelpers.cuh:235)
@@ -536,7 +538,7 @@ __global__ void sim_kernel(DevState S, int b0, int n_cand, int a_first){
             s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
         }
         __syncwarp();
-        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
+        kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
         if (EE){
             // running / final cost of this knot, not on the knots that close a defect (fpHelpers.cuh:259-265)
             if (l < kuka::NB && (kk < NBF - 1 || w == S.M - 1)){ cacc = ADD(cacc, ee_cost_share(l, s.ee, sxg, s.x, S.xTarget ? S.xTarget + (size_t)b*n : nullptr, s.u, k == N - 1, k >= N - 1 - (S.cost_shift ? S.cost_shift[b] : 0), S)); }
@@ -877,11 +879,12 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q){
         __syncwarp();
         kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
         const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
+        float Ib[36]; kuka::load_body_inertia<LANES>(S.I, Ib);
         if (l < n){ const float v = Q.xActual[b*n + l]; s.x[l] = v; cx[l] = v; }
         for (int k = 0; k < N-1; k++){
             if (l < m){ s.u[l] = cu[k*m + l]; }
             __syncwarp();
-            kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
+            kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix);
             if (l < kuka::NB){ s.xn[l] = FMA(S.dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(S.dt, s.qdd[l], s.x[l+kuka::NB]); }
             __syncwarp();
             if (l < n){ const float v = s.xn[l]; s.x[l] = v; cx[(k+1)*n + l] = v; }
@@ -930,11 +933,12 @@ __global__ void unit_dynamics_kernel(const float *I, const float *Tbody, float g
     SimGroupSmem &s = gsm[grp];
     kuka::init_ws<LANES>(s.ws, nullptr, sTb, grav);
     const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
+    float Ib[36]; kuka::load_body_inertia<LANES>(I, Ib);
     for (int k0 = blockIdx.x*GPW; k0 < nsamp; k0 += gridDim.x*GPW){
         const int k = k0 + grp < nsamp ? k0 + grp : nsamp - 1;         // tail: replay the last sample
         if (l < kuka::NX){ s.x[l] = x[k*kuka::NX + l]; } if (l < kuka::NU){ s.u[l] = u[k*kuka::NU + l]; }
         __syncwarp();
-        kuka::forward<LANES, false>(s.ws, nullptr, sI, s.x, s.u, s.qdd, fix);
+        kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix);
         if (l < kuka::NB){ qdd[k*kuka::NB + l] = s.qdd[l]; }
         __syncwarp();
     }

@@ -246,7 +246,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     } else {
         h->smem_bp = sizeof(BpSmem<kuka::NX, kuka::NU>);
         h->smem_sweep = SWEEP_SLOTS*sizeof(SweepSlot<kuka::NX>);
-        h->smem_sim = (2*36*kuka::NB + 16)*sizeof(float) + (size_t)M*(32/SIM_LANES)*sizeof(SimGroupSmem);
+        h->smem_sim = (36*kuka::NB + 16)*sizeof(float) + (size_t)(32/SIM_LANES)*sizeof(SimGroupSmem);
         h->smem_nis = NIS_CONST_FLOATS*sizeof(float) + NIS_WARPS*(32/NIS_LANES)*sizeof(NisGroupSmem);
         h->smem_udyn = 2*36*kuka::NB*sizeof(float) + (32/SIM_LANES)*sizeof(SimGroupSmem);
         h->smem_ugrad = 2*36*kuka::NB*sizeof(float) + (32/NIS_LANES)*sizeof(NisGroupSmem);
@@ -326,7 +326,7 @@ static int launch_reset(pddp_handle h, int ignore_first, int clear){
 // forward simulation of n_cand candidates of problems [b0, b0+nb): cost variant and lane shape picked here
 static void launch_sim_any(pddp_handle h, cudaStream_t st, int b0, int nb, int n_cand, int a_first = 0){
     DevState &S = h->S;
-    if (h->ops){ h->ops->launch_sim(&S, st, b0, nb, n_cand); return; } const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw), cta = 32*S.M;
+    if (h->ops){ h->ops->launch_sim(&S, st, b0, nb, n_cand); return; } const int gpw = 32 / h->sim_lanes, grid = nb*((n_cand + gpw - 1)/gpw)*S.M, cta = 32;
     if (h->sim_lanes == 32){
         if (S.ee){ sim_kernel<true, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); } else { sim_kernel<false, 32><<<grid, cta, h->smem_sim, st>>>(S, b0, n_cand, a_first); }
     } else {
