@@ -124,11 +124,16 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
         for (int c = 0; c < SWEEP_SLOTS && c < nslices; c++){ issue(c); }
     }
     __syncthreads();
-    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31;       // blockDim = 32 * (a_cnt / splits): every warp has a step size
+    const int a = a0 + (threadIdx.x >> 5), l = threadIdx.x & 31, lc = l < n ? l : n - 1;   // blockDim = 32 * (a_cnt / splits): every warp has a step size
     const float alpha = S.alpha[a];
     float *gx = S.x + ((size_t)b*S.A + a)*N*n;
     mbar_wait(&full[0], 0);
-    float xk = (l < n) ? slots[0].xp[l] : 0.f;      // x_a[0] = xp[0]
+    // lane l < n carries component l (the other lanes replay component n-1 and store nothing).  The recursion is one dependent chain
+    // per knot -- (x - xp) -> broadcast -> n fused multiply-adds -> three additions -- so everything that does not depend on x_a[k]
+    // (the column entries of A - BK, B du, the defect, xp[k+1]) is fetched BEFORE the chain, and xp[k] is the register that held
+    // xp[k+1] one knot earlier: no shared-memory load sits on the chain.
+    float xpk = slots[0].xp[lc];
+    float xk = xpk;                                  // x_a[0] = xp[0]
     if (l < n){ gx[l] = xk; }
     int to_boundary = NBF;                   // steps until k+1 is a shooting-interval boundary
     for (int c = 0; c < nslices; c++){
@@ -146,18 +151,23 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
             const float *xpn;
             if (kk == SWEEP_CH - 1){ mbar_wait(&full[(c+1) % SWEEP_SLOTS], ((c+1) / SWEEP_SLOTS) & 1); xpn = slots[(c+1) % SWEEP_SLOTS].xp; }
             else { xpn = sl.xp + (kk+1)*n; }
-            const float *Ak = sl.A + kk*n*n;
-            float dx = (l < n) ? SUB(xk, sl.xp[kk*n + l]) : 0.f;
+            const float *Ak = sl.A + kk*n*n + lc;
+            float ar[n];
+            #pragma unroll
+            for (int i = 0; i < n; i++){ ar[i] = Ak[n*i]; }
+            const float Bk = sl.B[kk*n + lc], dk = sl.d[kk*n + lc], xn = xpn[lc];
+            const float dx = SUB(xk, xpk);
+            float dxs[n];
+            #pragma unroll
+            for (int i = 0; i < n; i++){ dxs[i] = __shfl_sync(FULL, dx, i); }
             float val = 0.f;
             #pragma unroll
-            for (int i = 0; i < n; i++){ float dxi = __shfl_sync(FULL, dx, i); if (l < n){ val = FMA(Ak[l + n*i], dxi, val); } }
+            for (int i = 0; i < n; i++){ val = FMA(ar[i], dxs[i], val); }
             const bool onb = (--to_boundary == 0);
             if (onb){ to_boundary = NBF; }
-            if (l < n){
-                float tt = ADD(FMA(-alpha, sl.B[kk*n+l], val), onb ? sl.d[kk*n+l] : 0.f);
-                xk = ADD(xpn[l], tt);
-                gx[(k+1)*n + l] = xk;
-            }
+            const float tt = ADD(FMA(-alpha, Bk, val), onb ? dk : 0.f);
+            xk = ADD(xn, tt); xpk = xn;
+            if (l < n){ gx[(k+1)*n + l] = xk; }
         }
     }
 }
