@@ -223,7 +223,7 @@ def main():
         solver.solve_device(d_x0.data_ptr(), d_u0.data_ptr(), d_xg.data_ptr(), d_x.data_ptr(), d_u.data_ptr(), d_J.data_ptr(), d_a.data_ptr(), d_it.data_ptr(), 1, times)
         return times.copy()
 
-    groups = solver.set_groups(int(os.environ.get("PDDP_GROUPS", "4")))
+    groups = solver.set_groups(int(os.environ.get("PDDP_GROUPS", "2")))
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank); sampler.start()

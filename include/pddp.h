@@ -162,7 +162,7 @@ int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
 
 /* Number of independent problem groups, each iterated on its own CUDA stream so that one group's latency-bound kernels
  * (backward pass, sweep, selection) overlap another group's throughput-bound ones (sim, next-iteration setup).  Results do
- * not depend on it.  Default 4 (env PDDP_GROUPS) for batches of 8 problems or more, else 1; the per-phase entries of times_ms and
+ * not depend on it.  Default 2 (env PDDP_GROUPS) for batches of 4 problems or more, else 1; the per-phase entries of times_ms and
  * pddp_last_iteration_times need 1 group (the phases of different groups overlap, there is no per-phase time then).
  * Returns the value in effect. */
 int pddp_set_groups(pddp_handle h, int groups);

@@ -271,7 +271,14 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int b0){
             #pragma unroll
             for (int c = 0; c < m; c++){ a[c] = MUL(1.0f, __shfl_sync(FULL, (c & 1) ? h1 : h0, (t & 7) + 8*(c >> 1))); a[m + c] = (t == c) ? 1.f : 0.f; }
             BP_TRACE(3);
-            gauss_jordan_rows<m>(a, t);
+            float a_in[2*m];
+            #pragma unroll
+            for (int c = 0; c < 2*m; c++){ a_in[c] = a[c]; }
+            if (!gauss_jordan_rows<m, 32, true>(a, t)){
+                #pragma unroll
+                for (int c = 0; c < 2*m; c++){ a[c] = a_in[c]; }
+                gauss_jordan_rows<m, 32, false>(a, t);
+            }
             if (t < m){
                 *reinterpret_cast<float4*>(&s.Hinv[t*BP_RS]) = make_float4(a[m], a[m+1], a[m+2], a[m+3]);
                 *reinterpret_cast<float4*>(&s.Hinv[t*BP_RS + 4]) = make_float4(a[m+4], a[m+5], a[m+6], 0.f);

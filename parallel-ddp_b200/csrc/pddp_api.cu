@@ -189,7 +189,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     { const char *env = std::getenv("PDDP_SKIP_UNCHANGED"); h->skip_env = env && std::atoi(env) != 0; }
     { const char *env = std::getenv("PDDP_GRAPHS"); h->use_graphs = !(env && std::atoi(env) == 0); }
     { const char *env = std::getenv("PDDP_GRAPH_CHUNK"); const int v = env ? std::atoi(env) : 0; if (v >= 1 && v <= 1000){ h->graph_chunk = v; } }
-    { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 4; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
+    { const char *env = std::getenv("PDDP_GROUPS"); int g = env ? std::atoi(env) : 2; h->groups = (g >= 1 && g <= 8 && cfg->batch >= 2*g) ? g : 1; }
     DevState &S = h->S; std::memset(&S, 0, sizeof(S)); S.skip_unchanged = h->skip_env ? 1 : 0;
     const int B = cfg->batch, N = cfg->N, A = cfg->n_alpha, M = cfg->M, n = h->n, m = h->m;
     S.B = B; S.N = N; S.A = A; S.M = M; S.n = n; S.m = m; S.max_iter = cfg->max_iter; S.iter_cap = cfg->max_iter;
