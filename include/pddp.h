@@ -168,7 +168,7 @@ int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches);
 int pddp_set_groups(pddp_handle h, int groups);
 
 /* Per-iteration device times (ms) of the last pddp_solve* call that was given a times_ms array and ran as ONE problem group
- * (pddp_set_groups(h, 1); a batch below 8 problems always does): the entries of the reference's simTime / sweepTime / bpTime / nisTime
+ * (pddp_set_groups(h, 1); a batch below 4 problems always does): the entries of the reference's simTime / sweepTime / bpTime / nisTime
  * arrays (DDPWrappers.cuh:60-107).  sim includes the cost / defect reductions and the line search, as in the reference.  Returns the
  * number of iterations written (<= capacity); any array may be NULL. */
 int pddp_last_iteration_times(pddp_handle h, double *sim_ms, double *sweep_ms, double *bp_ms, double *nis_ms, int capacity);
