@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(BP_CTA, 2) bp_kernel(DevState S, int b0){
 constexpr int SIM_LANES = 16;
 struct SimGroupData {
     kuka::FwdWsT<false> ws;
-    float x[16], u[8], dx[16], qdd[8], xn[16], KT[kuka::NX*kuka::NU + 2];
+    __align__(16) float dx[16];
+    float x[16], u[8], qdd[8], xn[16];
     float ee[8];               // tool pose of the current knot (EE_COST)
 };
 // The two groups of a warp run the same instruction on their own workspaces: the workspaces are padded to an odd multiple
@@ -510,40 +511,41 @@ __global__ void __launch_bounds__(32, 14) sim_kernel(DevState S, int b0, int n_c
         if (w == 0){ const float v = gxp[l]; s.x[l] = v; if (live){ gx[l] = v; } }
         else { s.x[l] = gx[kStart*n + l]; }
     }
-    // prefetch registers for knot kStart
-    constexpr int KTQ = (n*m + LANES - 1) / LANES;
-    float rKT[KTQ], rdu = 0.f, rxp = 0.f, rup = 0.f;
-    #pragma unroll
-    for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = gKT[(size_t)kStart*n*m + (i < n*m ? i : n*m - 1)]; }
-    rdu = gdu[kStart*m + (l < m ? l : m - 1)]; rup = gup[kStart*m + (l < m ? l : m - 1)];
+    // prefetch registers for knot kStart: lane l < m holds row l of the gain K (14 values) -- the row it multiplies with x - xp
+    const int lm = l < m ? l : m - 1;
+    float kt[n], rdu = 0.f, rxp = 0.f, rup = 0.f;
+    auto load_gain = [&](int kq){
+        const float2 *src = reinterpret_cast<const float2*>(gKT + (size_t)kq*n*m + lm*n);
+        #pragma unroll
+        for (int c = 0; c < n; c += 2){ const float2 v = src[c >> 1]; kt[c] = v.x; kt[c+1] = v.y; }
+    };
+    load_gain(kStart);
+    rdu = gdu[kStart*m + lm]; rup = gup[kStart*m + lm];
     rxp = gxp[kStart*n + (l < n ? l : n - 1)];
     __syncwarp();
     #pragma unroll 1
     for (int kk = 0; kk < iters; kk++){
         const int k = kStart + kk;
-        // stage this knot's feedback data, start fetching the next knot's
-        #pragma unroll
-        for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; if (i < n*m){ s.KT[i] = rKT[q]; } }
         if (l < n){ s.dx[l] = SUB(s.x[l], rxp); }
         const float du_k = rdu, up_k = rup;
-        {
-            // unconditional, index-clamped loads straight into the loop-carried registers: a predicated load would be
-            // followed by a register move that waits for it, which exposes the global-memory latency in every step
-            const int kn = (kk + 1 < iters) ? k + 1 : k;
-            #pragma unroll
-            for (int q = 0; q < KTQ; q++){ const int i = l + LANES*q; rKT[q] = gKT[(size_t)kn*n*m + (i < n*m ? i : n*m - 1)]; }
-            rdu = gdu[kn*m + (l < m ? l : m - 1)]; rup = gup[kn*m + (l < m ? l : m - 1)];
-            rxp = gxp[kn*n + (l < n ? l : n - 1)];
-        }
+        // unconditional, index-clamped loads straight into the loop-carried registers: a predicated load would be
+        // followed by a register move that waits for it, which exposes the global-memory latency in every step
+        const int kn = (kk + 1 < iters) ? k + 1 : k;
+        rdu = gdu[kn*m + lm]; rup = gup[kn*m + lm];
+        rxp = gxp[kn*n + (l < n ? l : n - 1)];
         __syncwarp();
         // u = up - (alpha du + K dx)          (fpHelpers.cuh:210-219)
-        if (l < m){
+        {
+            float dxv[16];
+            #pragma unroll
+            for (int c = 0; c < 16; c += 4){ const float4 v = *reinterpret_cast<const float4*>(&s.dx[c]); dxv[c] = v.x; dxv[c+1] = v.y; dxv[c+2] = v.z; dxv[c+3] = v.w; }
             float Kdx = 0.f;
             #pragma unroll
-            for (int c = 0; c < n; c++){ Kdx = FMA(s.KT[c + l*n], s.dx[c], Kdx); }
+            for (int c = 0; c < n; c++){ Kdx = FMA(kt[c], dxv[c], Kdx); }
             const float uu = SUB(up_k, FMA(alpha, du_k, Kdx));
-            s.u[l] = uu; if (live){ gu[k*m + l] = uu; }
+            if (l < m){ s.u[l] = uu; if (live){ gu[k*m + l] = uu; } }
         }
+        load_gain(kn);                                          // the next knot's row, a whole dynamics evaluation ahead of its use
         __syncwarp();
         kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix, EE ? s.ee : nullptr);
         if (EE){
