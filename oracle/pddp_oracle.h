@@ -53,6 +53,8 @@ typedef struct {
     int   use_xtarget;           /* EE_COST: the nominal-state terms measure x from xTarget (non-null on the receding-horizon path, MPCHelpers.cuh:900) */
     float xTarget[ORC_MAX_N];
     int   final_cost_shift;      /* EE_COST: finalCostShift of runiLQR_MPC_GPU (MPCHelpers.cuh:876): the pose terms take their final weights from knot N-1-shift on */
+    int   use_limits;            /* USE_LIMITS_FLAG config.cuh:171-173: quadratic penalties beyond the joint / velocity / torque limits (joint-space cost) */
+    float Q_PL, Q_VL, R_TL;      /* cost_arm.cuh:26-30 */
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */

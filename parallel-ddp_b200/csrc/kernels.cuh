@@ -432,6 +432,24 @@ constexpr int SIM_GROUP_FLOATS = (int)(sizeof(SimGroupData) / 4), SIM_PAD = (48 
 struct SimGroupSmem : SimGroupData { float pad[SIM_PAD ? SIM_PAD : 32]; };
 static_assert((sizeof(SimGroupSmem) / 4) % 32 == 16, "group workspaces must sit 16 banks apart");
 
+// USE_LIMITS_FLAG (plants/cost_arm.cuh:11-94): qr * quadPen<dLevel>(val, limit) of entry `ind` of [x; u] -- zero inside 0.8 x the
+// iiwa14's joint / velocity / torque limit, 0.5 delta^2 (dLevel 0) or +-delta (dLevel 1) beyond it, delta = |val| - limit.  The
+// reference forms 0.5*delta*delta in double: both products are exact there, so its float result is MUL(MUL(0.5f, delta), delta).
+// Rounding of the reference's device build (SASS of its costKern / costGradientHessianKern built with USE_LIMITS_FLAG 1): every penalty is
+// rounded on its own and selected against 0, so nothing is contracted into the sums -- except that `cost = 0.5*cost; cost += term_0` is one
+// fma(cost, 0.5, term_0); the other terms, and the gradient's `gk[i] += term`, are plain additions.
+__device__ __forceinline__ float limit_of(int ind){
+    constexpr int np = kuka::NB, n = kuka::NX;
+    if (ind < np){ return (float)(ind == 6 ? 3.05432619099 * 0.8 : ((ind & 1) ? 2.09439510239 * 0.8 : 2.96705972839 * 0.8)); }
+    if (ind < n){ const int j = ind - np; return (float)(j > 4 ? 2.356194 * 0.8 : (j == 4 ? 2.268928 * 0.8 : (j == 3 ? 1.308996 * 0.8 : (j == 2 ? 1.745329 * 0.8 : 1.483529 * 0.8)))); }
+    return (float)(300.0 * 0.8);
+}
+template <int DLEVEL>
+__device__ __forceinline__ float limit_pen(float val, int ind){
+    const float delta = SUB(fabsf(val), limit_of(ind));
+    return delta < 0.f ? 0.f : (DLEVEL == 0 ? MUL(MUL(0.5f, delta), delta) : (val < 0.f ? -delta : delta));
+}
+__device__ __forceinline__ float limit_weight(int ind, const DevState &S){ return ind < kuka::NB ? S.Q_PL : (ind < kuka::NX ? S.Q_VL : S.R_TL); }
 // joint-space quadratic cost of one knot (plants/cost_arm.cuh:128-153), evaluated by one lane
 __device__ __forceinline__ float cost_knot(const float *x, const float *u, const float *xg, bool final_knot, const DevState &S){
     float cost = 0.f;
@@ -440,6 +458,12 @@ __device__ __forceinline__ float cost_knot(const float *x, const float *u, const
     } else {
         for (int i = 0; i < kuka::NX; i++){ float dl = SUB(x[i], xg[i]); cost = FMA(MUL(i < kuka::NB ? S.Q1 : S.Q2, dl), dl, cost); }
         for (int i = 0; i < kuka::NU; i++){ cost = FMA(MUL(S.R, u[i]), u[i], cost); }
+    }
+    if (S.use_limits){
+        cost = FMA(cost, 0.5f, MUL(limit_weight(0, S), limit_pen<0>(x[0], 0)));
+        for (int i = 1; i < kuka::NX; i++){ cost = ADD(cost, MUL(limit_weight(i, S), limit_pen<0>(x[i], i))); }
+        if (!final_knot){ for (int i = 0; i < kuka::NU; i++){ cost = ADD(cost, MUL(limit_weight(kuka::NX + i, S), limit_pen<0>(u[i], kuka::NX + i))); } }
+        return cost;
     }
     return MUL(0.5f, cost);
 }
@@ -748,8 +772,11 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     // joint-space cost; the end-effector cost needs the tool pose and follows the gradient below
     if (!S.ee){
         for (int e = l; e < nm; e += LANES){
-            if (e < n){ gg[e] = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
-            else { gg[e] = fin ? 0.f : MUL(S.R, s.u[e-n]); }
+            float gv;
+            if (e < n){ gv = MUL(fin ? (e < np ? S.QF1 : S.QF2) : (e < np ? S.Q1 : S.Q2), SUB(s.x[e], xg[e])); }
+            else { gv = fin ? 0.f : MUL(S.R, s.u[e-n]); }
+            if (S.use_limits && (e < n || !fin)){ gv = ADD(gv, MUL(limit_weight(e, S), limit_pen<1>(e < n ? s.x[e] : s.u[e-n], e))); }      // cost_arm.cuh:176-179,197-200
+            gg[e] = gv;
         }
     }
     if (write_H && !S.ee){

@@ -32,6 +32,8 @@ def run(N, *args):
         exe, args = os.path.join(REF, f"ref_mpc_ee_N{N}"), ("mpc",) + tuple(args[1:])
         if "CS" in args:                                # use_cost_shift = 1: the flag follows the output file on ref_mpc's command line
             args = tuple(a for a in args if a != "CS") + (1,)
+    if args and str(args[0]).startswith("lim_"):         # joint-space cost with the limit penalties (ref_driver.cu built with -DUSE_LIMITS_FLAG=1)
+        exe, args = os.path.join(REF, f"ref_lim_N{N}"), (args[0][4:],) + tuple(args[1:])
     if args and str(args[0]).startswith("ee_"):          # end-effector cost build (EE_COST 1): oracle/ref_harness/ref_ee.cu
         exe, args = os.path.join(REF, f"ref_ee_N{N}"), (args[0][3:],) + tuple(args[1:])
     print("+", exe, *args, flush=True)
@@ -53,7 +55,10 @@ def jobs(hw):
            (32, ("trace", t, 3, 0.0001, 1), f"trace_{t}_N32_s3_tol1e-4"),
            (128, ("trace", t, 0, 0.0, 1), f"trace_{t}_N128_s0_tol0"),
            # end-effector cost: cost / gradient / Hessian of costGradientHessianKern (G) / ...Threaded (H) on random states
-           (32, ("ee_unit", t, 64, 7), f"ee_unit_{t}")]
+           (32, ("ee_unit", t, 64, 7), f"ee_unit_{t}"),
+           # USE_LIMITS_FLAG 1: cost / gradient on random states (host-evaluated in both dumps), every phase of the first iterations
+           (32, ("lim_unit", t, 64, 7), f"lim_unit_{t}"),
+           (32, ("lim_trace", t, 4, 0.0, 2), f"lim_trace_{t}_N32_s4_tol0")]
     # PLANT 1-3 (oracle/ref_harness/adapt_plant.cuh): plant functions + integrator gradient on random states, traces of whole solves
     for cfg, seeds in (("p1_i3_N32_a1", (0,)), ("p1_i2_N32_a4", (1,)), ("p2_i3_N64_a8", (0, 2)), ("p2_i1_N32_a8", (1,)),
                        ("p3_i3_N64_a16", (0,)), ("p3_i2_N32_a16", (1,))):
@@ -74,6 +79,7 @@ def jobs(hw):
                 (32, ("mpc", 5, 8, 2, 4), "mpc_G_N32_s5"),
                 (128, ("mpc", 6, 5, 3, 6), "mpc_G_N128_s6"),
                 # end-effector cost: whole solves of the reference's EE_COST build
+                (32, ("lim_solve", "G", 0, 8, 0.0), "lim_solve_G_N32_s0-7_tol0"),
                 (32, ("ee_solve", "G", 0, 4, 0.0), "ee_solve_G_N32_s0-3_tol0"),
                 (128, ("ee_solve", "G", 0, 2, 0.0), "ee_solve_G_N128_s0-1_tol0"),
                 (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1"),

@@ -25,7 +25,8 @@ class Cfg(C.Structure):
                 ("Q1", F), ("Q2", F), ("R", F), ("QF1", F), ("QF2", F),
                 ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float), ("ee_cost", C.c_int)] + \
                [(k, F) for k in ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")] + \
-               [("use_xtarget", C.c_int), ("xTarget", F * 16), ("final_cost_shift", C.c_int)]
+               [("use_xtarget", C.c_int), ("xTarget", F * 16), ("final_cost_shift", C.c_int),
+                ("use_limits", C.c_int), ("Q_PL", F), ("Q_VL", F), ("R_TL", F)]
 
 
 class Ws(C.Structure):

@@ -16,7 +16,8 @@ o2 = s.runiLQR_GPU(o["x"], o["u"], xg, forwardRolloutFlag=1, clearVarsFlag=0, KT
 s.mpc_init(x0, u0 * 0 + 0.01)
 for st in range(2):
     s.mpc_step(s.mpc_x[:, 0].copy(), xg, 0 if st == 0 else 2, 2, clear_vars=1 if st == 0 else 0)
-print("done", o["iters"], o2["iters"])
+sl = pddp.Solver(pddp.default_config_kuka(N, B, max_iter=3, use_limits=1)); ol_ = sl.runiLQR_GPU(x0, u0, xg)      # limit penalties (USE_LIMITS_FLAG 1)
+print("done", o["iters"], o2["iters"], ol_["iters"])
 # end-effector cost: cold solve, rollout start, receding horizon with xTarget
 xe = np.zeros((B, 14), np.float32); xe[:, :6] = (0.3638, 0.0, 1.0628, 1.570795, 0.0, 1.570795)
 w = dict(zip(pddp.EE_WEIGHT_NAMES, (0.1, 0.01, 1000.0, 10.0, 1e-4, 0.1, 1000.0, 1e-3, 1.0)))
