@@ -58,6 +58,10 @@ typedef struct pddp_config {
                                                           gradient (plants/cost_arm.cuh:11-94,136-150,176-200; the Hessian is not touched) */
     float lim_Q_pos, lim_Q_vel, lim_R_tau;             /* Q_PL, Q_VL, R_TL of cost_arm.cuh:26-30: penalty weights of the position / velocity / torque
                                                           limits (100 each; named apart from the reference's macros so that the header shim can assign them) */
+    int   use_smooth_abs;                              /* USE_SMOOTH_ABS (config.cuh:174-176; EE_COST 1): the pose term c of a knot's cost becomes
+                                                          sqrt(2 c + alpha^2) - alpha and its gradient is divided by sqrt(2 c + alpha^2)
+                                                          (plants/cost_arm.cuh:218-220,242-252; the Gauss-Newton Hessian is not touched) */
+    double smooth_abs_alpha;                           /* SMOOTH_ABS_ALPHA (cost_arm.cuh:119-121, 0.2): a double, as the reference squares it in double */
 } pddp_config;
 
 typedef struct pddp_solver *pddp_handle;

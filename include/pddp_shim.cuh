@@ -165,6 +165,12 @@ typedef float algType;
 #ifndef USE_LIMITS_FLAG
 #define USE_LIMITS_FLAG 0      // config.cuh:171-173
 #endif
+#ifndef USE_SMOOTH_ABS
+#define USE_SMOOTH_ABS 0       // config.cuh:174-176
+#endif
+#ifndef SMOOTH_ABS_ALPHA
+#define SMOOTH_ABS_ALPHA 0.2    // plants/cost_arm.cuh:119-121
+#endif
 #ifndef R_TL
 #define R_TL 100.0             // plants/cost_arm.cuh:26-30
 #define Q_PL 100.0
@@ -200,6 +206,7 @@ void allocateMemory_GPU(T ***d_x, T ***h_d_x, T **d_xp, T **d_xp2, T ***d_u, T *
     cfg.ee_cost = EE_COST; cfg.Q_EE1 = (float)_Q_EE1; cfg.Q_EE2 = (float)_Q_EE2; cfg.QF_EE1 = (float)_QF_EE1; cfg.QF_EE2 = (float)_QF_EE2; cfg.R_EE = (float)_R_EE;
     cfg.Q_xdEE = (float)_Q_xdEE; cfg.QF_xdEE = (float)_QF_xdEE; cfg.Q_xEE = (float)_Q_xEE; cfg.QF_xEE = (float)_QF_xEE;
     cfg.use_limits = USE_LIMITS_FLAG; cfg.lim_Q_pos = (float)Q_PL; cfg.lim_Q_vel = (float)Q_VL; cfg.lim_R_tau = (float)R_TL;
+    cfg.use_smooth_abs = USE_SMOOTH_ABS; cfg.smooth_abs_alpha = SMOOTH_ABS_ALPHA;
     pddp_handle h = nullptr;
     if (pddp_create(&cfg, &h) != 0){ pddp_shim_die(nullptr, "pddp_create"); }
     *d_x = reinterpret_cast<T**>(h);                                   // the handle travels in the d_x slot

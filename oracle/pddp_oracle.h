@@ -55,6 +55,8 @@ typedef struct {
     int   final_cost_shift;      /* EE_COST: finalCostShift of runiLQR_MPC_GPU (MPCHelpers.cuh:876): the pose terms take their final weights from knot N-1-shift on */
     int   use_limits;            /* USE_LIMITS_FLAG config.cuh:171-173: quadratic penalties beyond the joint / velocity / torque limits (joint-space cost) */
     float Q_PL, Q_VL, R_TL;      /* cost_arm.cuh:26-30 */
+    int   use_smooth_abs;        /* USE_SMOOTH_ABS config.cuh:174-176 (EE_COST): pose term sqrt(2 c + alpha^2) - alpha, cost_arm.cuh:218-220,242-252 */
+    float sa_alpha, sa_alpha2;   /* (T)SMOOTH_ABS_ALPHA and (T)(SMOOTH_ABS_ALPHA*SMOOTH_ABS_ALPHA) (the product is formed in double), cost_arm.cuh:119-121 */
 } orc_cfg;
 
 /* work arrays of one problem, reference layouts */

@@ -39,7 +39,8 @@ class Config(C.Structure):
                 ("exp_red_min", C.c_float), ("exp_red_max", C.c_float), ("max_defect", C.c_float), ("tol_cost", C.c_float),
                 ("Q1", C.c_float), ("Q2", C.c_float), ("R", C.c_float), ("QF1", C.c_float), ("QF2", C.c_float), ("gravity", C.c_float),
                 ("ee_cost", C.c_int)] + [(k, C.c_float) for k in EE_WEIGHT_NAMES] + \
-               [("use_limits", C.c_int), ("lim_Q_pos", C.c_float), ("lim_Q_vel", C.c_float), ("lim_R_tau", C.c_float)]
+               [("use_limits", C.c_int), ("lim_Q_pos", C.c_float), ("lim_Q_vel", C.c_float), ("lim_R_tau", C.c_float),
+                ("use_smooth_abs", C.c_int), ("smooth_abs_alpha", C.c_double)]
 
 
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",

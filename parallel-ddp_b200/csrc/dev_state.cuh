@@ -22,6 +22,7 @@ struct DevState {
     float rho_min, rho_max, rho_factor, inv_rho_factor, exp_red_min, exp_red_max, max_defect;
     float Q1, Q2, R, QF1, QF2;
     int use_limits; float Q_PL, Q_VL, R_TL;      // USE_LIMITS_FLAG (plants/cost_arm.cuh:11-94), joint-space cost of the arm
+    int smooth_abs; float sa_alpha, sa_alpha2;   // USE_SMOOTH_ABS (plants/cost_arm.cuh:218-220,242-252), end-effector cost
     // model constants (device)
     const float *I, *Tbody, *alpha;
     // trajectories

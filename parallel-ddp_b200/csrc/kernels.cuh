@@ -477,6 +477,7 @@ __device__ __forceinline__ float ee_pose_cost(const float *ee, const float *goal
         const float dl = SUB(ee[i], goal[i]), Q = fin ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
         cost = FMA(MUL(MUL(0.5f, Q), dl), dl, cost);
     }
+    if (S.smooth_abs){ cost = SUB(sqrtf(FMA(2.f, cost, S.sa_alpha2)), S.sa_alpha); }      // USE_SMOOTH_ABS, cost_arm.cuh:218-220
     return cost;
 }
 // `cost += nominalStateCost(...)` :263-270
@@ -805,6 +806,15 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
                 for (int i = 0; i < 6; i++){
                     const float dl = SUB(s.ee[i], xg[i]), Q = finp ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
                     v2 = FMA(MUL(Q, dl), s.dee[r*6+i], v2);
+                }
+                if (S.smooth_abs){                                   // USE_SMOOTH_ABS, cost_arm.cuh:242-252: d/dq of sqrt(2 c + alpha^2)
+                    float v3 = 0.f;
+                    #pragma unroll
+                    for (int i = 0; i < 6; i++){
+                        const float dl = SUB(s.ee[i], xg[i]), Q = finp ? (i < 3 ? S.QF_EE1 : S.QF_EE2) : (i < 3 ? S.Q_EE1 : S.Q_EE2);
+                        v3 = FMA(MUL(Q, dl), dl, v3);
+                    }
+                    v2 = DIV(v2, sqrtf(ADD(v3, S.sa_alpha2)));
                 }
                 val = ADD(val, v2);
             }

@@ -80,6 +80,7 @@ extern "C" void pddp_default_config_kuka(pddp_config *c, int N, int batch){
     c->Q_EE1 = (float)0.1; c->Q_EE2 = 0.f; c->QF_EE1 = (float)1000.0; c->QF_EE2 = 0.f; c->R_EE = (float)0.0001;
     c->Q_xdEE = (float)0.1; c->QF_xdEE = (float)1000.0; c->Q_xEE = 0.f; c->QF_xEE = 0.f;
     c->use_limits = 0; c->lim_Q_pos = (float)100.0; c->lim_Q_vel = (float)100.0; c->lim_R_tau = (float)100.0;    // plants/cost_arm.cuh:26-30
+    c->use_smooth_abs = 0; c->smooth_abs_alpha = 0.2;                                                   // plants/cost_arm.cuh:119-121
 }
 
 // ---------------------------------------------------------------------------------------------------- plant plug-ins
@@ -203,6 +204,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2; S.grav = cfg->gravity;
     S.ee = cfg->ee_cost ? 1 : 0;
     S.use_limits = (cfg->use_limits && cfg->plant == PDDP_PLANT_KUKA && !cfg->ee_cost) ? 1 : 0; S.Q_PL = cfg->lim_Q_pos; S.Q_VL = cfg->lim_Q_vel; S.R_TL = cfg->lim_R_tau;
+    S.smooth_abs = (cfg->use_smooth_abs && S.ee) ? 1 : 0; S.sa_alpha = (float)cfg->smooth_abs_alpha; S.sa_alpha2 = (float)(cfg->smooth_abs_alpha*cfg->smooth_abs_alpha);
     S.a_first = 0; S.a_cnt = A;
     S.Q_EE1 = cfg->Q_EE1; S.Q_EE2 = cfg->Q_EE2; S.QF_EE1 = cfg->QF_EE1; S.QF_EE2 = cfg->QF_EE2; S.R_EE = cfg->R_EE;
     S.Q_xdEE = cfg->Q_xdEE; S.QF_xdEE = cfg->QF_xdEE; S.Q_xEE = cfg->Q_xEE; S.QF_xEE = cfg->QF_xEE;

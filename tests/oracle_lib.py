@@ -26,7 +26,8 @@ class Cfg(C.Structure):
                 ("I", F * 252), ("Tbody", F * 252), ("gravity", C.c_float), ("ee_cost", C.c_int)] + \
                [(k, F) for k in ("Q_EE1", "Q_EE2", "QF_EE1", "QF_EE2", "R_EE", "Q_xdEE", "QF_xdEE", "Q_xEE", "QF_xEE")] + \
                [("use_xtarget", C.c_int), ("xTarget", F * 16), ("final_cost_shift", C.c_int),
-                ("use_limits", C.c_int), ("Q_PL", F), ("Q_VL", F), ("R_TL", F)]
+                ("use_limits", C.c_int), ("Q_PL", F), ("Q_VL", F), ("R_TL", F),
+                ("use_smooth_abs", C.c_int), ("sa_alpha", F), ("sa_alpha2", F)]
 
 
 class Ws(C.Structure):
