@@ -345,9 +345,9 @@ def main():
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         sim_flop = B * N_ALPHA * (N_KNOTS - 1) * 12.9e3 * MAX_ITER; nis_flop = B * N_KNOTS * 184e3 * MAX_ITER
         out["other_kernels"] = [
-            {"kernel": "sim_kernel (+select)", "bound": "fp32 issue / latency", "achieved": sim_flop / (ph["sim+select"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+            {"kernel": "sim_kernel (+select)", "bound": "shared-memory pipe / fp32 issue (ncu: 67 % / 59 % of peak)", "achieved": sim_flop / (ph["sim+select"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
              "frac": sim_flop / (ph["sim+select"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"},
-            {"kernel": "nis_kernel", "bound": "fp32 issue / latency", "achieved": nis_flop / (ph["nis"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+            {"kernel": "nis_kernel", "bound": "fp32 issue / latency (16 warps per SM)", "achieved": nis_flop / (ph["nis"] * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
              "frac": nis_flop / (ph["nis"] * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal FP32 (no tensor cores: bit-exact fp32 chains)"}]
         # DRAM traffic of the backward pass: one ncu --set full capture per kernel version (tools/gpu_bp_traffic.sh), not something a bench
         # run can measure itself; the capture records the hash of the kernel source it was taken from, and a capture of an older
