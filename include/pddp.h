@@ -53,9 +53,10 @@ typedef struct pddp_config {
     float Q_EE1, Q_EE2, QF_EE1, QF_EE2, R_EE;          /* plants/cost_arm.cuh:106-111: running / final weights of the position (1) and
                                                           orientation (2) errors, control weight */
     float Q_xdEE, QF_xdEE, Q_xEE, QF_xEE;              /* cost_arm.cuh:112-115: running / final weights on joint velocities (xd) and angles (x) */
-    int   use_limits;                                  /* USE_LIMITS_FLAG (config.cuh:171-173; PLANT 4, joint-space cost): quadratic penalties
-                                                          beyond 0.8 x the iiwa14's joint, velocity and torque limits in the cost and its
-                                                          gradient (plants/cost_arm.cuh:11-94,136-150,176-200; the Hessian is not touched) */
+    int   use_limits;                                  /* USE_LIMITS_FLAG (config.cuh:171-173; PLANT 4, either cost): quadratic penalties beyond
+                                                          0.8 x the iiwa14's joint, velocity and torque limits in the cost and its gradient
+                                                          (plants/cost_arm.cuh:11-94,136-150,176-200: joint-space cost, Hessian untouched;
+                                                          :289-291,310-312,341-343,374-376: end-effector cost, Hessian diagonal included) */
     float lim_Q_pos, lim_Q_vel, lim_R_tau;             /* Q_PL, Q_VL, R_TL of cost_arm.cuh:26-30: penalty weights of the position / velocity / torque
                                                           limits (100 each; named apart from the reference's macros so that the header shim can assign them) */
     int   use_smooth_abs;                              /* USE_SMOOTH_ABS (config.cuh:174-176; EE_COST 1): the pose term c of a knot's cost becomes

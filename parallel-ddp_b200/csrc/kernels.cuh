@@ -447,7 +447,7 @@ __device__ __forceinline__ float limit_of(int ind){
 template <int DLEVEL>
 __device__ __forceinline__ float limit_pen(float val, int ind){
     const float delta = SUB(fabsf(val), limit_of(ind));
-    return delta < 0.f ? 0.f : (DLEVEL == 0 ? MUL(MUL(0.5f, delta), delta) : (val < 0.f ? -delta : delta));
+    return delta < 0.f ? 0.f : (DLEVEL == 0 ? MUL(MUL(0.5f, delta), delta) : (DLEVEL == 1 ? (val < 0.f ? -delta : delta) : 1.f));
 }
 __device__ __forceinline__ float limit_weight(int ind, const DevState &S){ return ind < kuka::NB ? S.Q_PL : (ind < kuka::NX ? S.Q_VL : S.R_TL); }
 // joint-space quadratic cost of one knot (plants/cost_arm.cuh:128-153), evaluated by one lane
@@ -486,13 +486,22 @@ __device__ __forceinline__ float ee_add_nominal(const float *x, const float *xt,
     const float dq = xt ? SUB(x[ind], xt[ind]) : x[ind], dqd = xt ? SUB(x[ind + kuka::NB], xt[ind + kuka::NB]) : x[ind + kuka::NB];
     return FMA(0.5f, FMA(MUL(Qq, dq), dq, MUL(MUL(Qqd, dqd), dqd)), cost);
 }
+// USE_LIMITS_FLAG inside the end-effector cost (:289-291,310-312): joint `ind` adds the penalties of its angle, its velocity and its torque
+// (the torque also on the final knot, unlike the joint-space cost)
+__device__ __forceinline__ float ee_add_limits(const float *x, const float *u, int ind, float cost, const DevState &S){
+    cost = ADD(cost, MUL(S.Q_PL, limit_pen<0>(x[ind], ind)));
+    cost = ADD(cost, MUL(S.Q_VL, limit_pen<0>(x[ind + kuka::NB], ind + kuka::NB)));
+    return ADD(cost, MUL(S.R_TL, limit_pen<0>(u[ind], ind + kuka::NX)));
+}
 // joint `ind`'s share of one knot (split costFunc :283-303)
 __device__ __forceinline__ float ee_cost_share(int ind, const float *ee, const float *goal, const float *x, const float *xt, const float *u, bool fin, bool fin_pose, const DevState &S){
     float cost = 0.f;
     if (ind == 0){ cost = ADD(cost, ee_pose_cost(ee, goal, fin_pose, S)); }
     const float Rk = fin ? 0.f : S.R_EE;
     cost = FMA(MUL(MUL(0.5f, Rk), u[ind]), u[ind], cost);
-    return ee_add_nominal(x, xt, ind, fin, cost, S);
+    cost = ee_add_nominal(x, xt, ind, fin, cost, S);
+    if (S.use_limits){ cost = ee_add_limits(x, u, ind, cost, S); }
+    return cost;
 }
 
 // LANES = 16: two candidates per warp, the throughput shape (27 % faster than 32 lanes once every scheduler has several warps).
@@ -820,6 +829,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
             }
             if (r < n){ val = ADD(val, MUL((r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (fin ? S.QF_xdEE : S.Q_xdEE), xt ? SUB(s.x[r], xt[r]) : s.x[r])); }   // the reference's build leaves this product unfused (pinned by its GPU unit dump)
             else { val = FMA(Rk, s.u[r-n], val); }
+            if (S.use_limits){ val = ADD(val, MUL(limit_weight(r, S), limit_pen<1>(r < n ? s.x[r] : s.u[r-n], r))); }      // cost_arm.cuh:341-343
             gg[r] = val;
         }
         float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
@@ -829,7 +839,10 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
                 #pragma unroll
                 for (int j = 0; j < 6; j++){ val = FMA(s.dee[r*6+j], s.dee[cc*6+j], val); }
             }
-            if (r == cc){ val = ADD(val, (r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (r < n ? (fin ? S.QF_xdEE : S.Q_xdEE) : Rk)); }
+            if (r == cc){
+                val = ADD(val, (r < np) ? (fin ? S.QF_xEE : S.Q_xEE) : (r < n ? (fin ? S.QF_xdEE : S.Q_xdEE) : Rk));
+                if (S.use_limits){ val = ADD(val, MUL(limit_weight(r, S), limit_pen<2>(r < n ? s.x[r] : s.u[r-n], r))); }      // cost_arm.cuh:374-376
+            }
             gH[e] = val;
         }
         // initialisation without a rollout: the knot's cost (costGrad's d_JT, :383-388; single-valued costFunc :306-325)
@@ -839,6 +852,7 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
                 if (ind == 0){ cost = ADD(cost, ee_pose_cost(s.ee, xg, finp, S)); }
                 cost = FMA(MUL(MUL(0.5f, Rk), s.u[ind]), s.u[ind], cost);
                 cost = ee_add_nominal(s.x, xt, ind, fin, cost, S);
+                if (S.use_limits){ cost = ee_add_limits(s.x, s.u, ind, cost, S); }
             }
             S.costk[((size_t)b*S.A + 0)*N + k] = cost;
         }

@@ -203,7 +203,7 @@ extern "C" int pddp_create(const pddp_config *cfg, pddp_handle *out){
     S.exp_red_min = cfg->exp_red_min; S.exp_red_max = cfg->exp_red_max; S.max_defect = cfg->max_defect;
     S.Q1 = cfg->Q1; S.Q2 = cfg->Q2; S.R = cfg->R; S.QF1 = cfg->QF1; S.QF2 = cfg->QF2; S.grav = cfg->gravity;
     S.ee = cfg->ee_cost ? 1 : 0;
-    S.use_limits = (cfg->use_limits && cfg->plant == PDDP_PLANT_KUKA && !cfg->ee_cost) ? 1 : 0; S.Q_PL = cfg->lim_Q_pos; S.Q_VL = cfg->lim_Q_vel; S.R_TL = cfg->lim_R_tau;
+    S.use_limits = (cfg->use_limits && cfg->plant == PDDP_PLANT_KUKA) ? 1 : 0; S.Q_PL = cfg->lim_Q_pos; S.Q_VL = cfg->lim_Q_vel; S.R_TL = cfg->lim_R_tau;
     S.smooth_abs = (cfg->use_smooth_abs && S.ee) ? 1 : 0; S.sa_alpha = (float)cfg->smooth_abs_alpha; S.sa_alpha2 = (float)(cfg->smooth_abs_alpha*cfg->smooth_abs_alpha);
     S.a_first = 0; S.a_cnt = A;
     S.Q_EE1 = cfg->Q_EE1; S.Q_EE2 = cfg->Q_EE2; S.QF_EE1 = cfg->QF_EE1; S.QF_EE2 = cfg->QF_EE2; S.R_EE = cfg->R_EE;

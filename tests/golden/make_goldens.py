@@ -32,6 +32,8 @@ def run(N, *args):
         exe, args = os.path.join(REF, f"ref_mpc_ee_N{N}"), ("mpc",) + tuple(args[1:])
         if "CS" in args:                                # use_cost_shift = 1: the flag follows the output file on ref_mpc's command line
             args = tuple(a for a in args if a != "CS") + (1,)
+    if args and str(args[0]).startswith("eelim_"):       # end-effector cost with the limit penalties (ref_ee.cu built with -DUSE_LIMITS_FLAG=1)
+        exe, args = os.path.join(REF, f"ref_eelim_N{N}"), (args[0][6:],) + tuple(args[1:])
     if args and str(args[0]).startswith("eesa_"):        # end-effector cost with the smooth-abs pose term (ref_ee.cu built with -DUSE_SMOOTH_ABS=1)
         exe, args = os.path.join(REF, f"ref_eesa_N{N}"), (args[0][5:],) + tuple(args[1:])
     if args and str(args[0]).startswith("lim_"):         # joint-space cost with the limit penalties (ref_driver.cu built with -DUSE_LIMITS_FLAG=1)
@@ -60,6 +62,7 @@ def jobs(hw):
            (32, ("ee_unit", t, 64, 7), f"ee_unit_{t}"),
            # USE_LIMITS_FLAG 1: cost / gradient on random states (host-evaluated in both dumps), every phase of the first iterations
            (32, ("eesa_unit", t, 64, 7), f"eesa_unit_{t}"),       # USE_SMOOTH_ABS 1
+           (32, ("eelim_unit", t, 64, 7), f"eelim_unit_{t}"),     # EE_COST 1 + USE_LIMITS_FLAG 1
            (32, ("lim_unit", t, 64, 7), f"lim_unit_{t}"),
            (32, ("lim_trace", t, 4, 0.0, 2), f"lim_trace_{t}_N32_s4_tol0")]
     # PLANT 1-3 (oracle/ref_harness/adapt_plant.cuh): plant functions + integrator gradient on random states, traces of whole solves
@@ -84,6 +87,7 @@ def jobs(hw):
                 # end-effector cost: whole solves of the reference's EE_COST build
                 (32, ("lim_solve", "G", 0, 8, 0.0), "lim_solve_G_N32_s0-7_tol0"),
                 (32, ("eesa_solve", "G", 0, 4, 0.0), "eesa_solve_G_N32_s0-3_tol0"),
+                (32, ("eelim_solve", "G", 0, 4, 0.0), "eelim_solve_G_N32_s0-3_tol0"),
                 (32, ("ee_solve", "G", 0, 4, 0.0), "ee_solve_G_N32_s0-3_tol0"),
                 (128, ("ee_solve", "G", 0, 2, 0.0), "ee_solve_G_N128_s0-1_tol0"),
                 (32, ("ee_warm", "G", 1, 0.0001, 0.0), "ee_warm_G_N32_s1"),
