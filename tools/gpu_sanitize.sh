@@ -43,5 +43,6 @@ for plant, integ, A in ((1, 3, 1), (2, 2, 8), (3, 3, 16), (3, 1, 4)):
     print("done plant", plant, integ, op["iters"])
 PY
 for tool in memcheck racecheck synccheck; do
-  echo "== $tool"; timeout 500 compute-sanitizer --tool $tool python /tmp/san.py 2>&1 | grep -E "ERROR SUMMARY|RACECHECK SUMMARY|done|Error|hazard" | head -8
+  echo "== $tool"; timeout 500 compute-sanitizer --tool $tool python /tmp/san.py > /tmp/san_$tool.txt 2>&1
+  grep -E "^done|ERROR SUMMARY|RACECHECK SUMMARY" /tmp/san_$tool.txt; echo "hazard / error records: $(grep -cE "hazard detected|Invalid|Error:" /tmp/san_$tool.txt)"; grep -E "hazard detected|Invalid" /tmp/san_$tool.txt | sort | uniq -c | head -5
 done
