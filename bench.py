@@ -255,6 +255,18 @@ def main():
     barrier()
     e2e_s = time.time() - t0
     clocks = sampler.stop()
+    # informational, rank 0 at N=1 only and NOT the headline: the opt-in pddp_set_skip_unchanged -- after a rejected line search the
+    # trajectory, hence AB / H / g, are unchanged, and the gradient refresh returns at once instead of recomputing identical values as
+    # the reference does (bit-identical results; 47 % of this workload's iterations reject)
+    optin = None
+    if world == 1 and not BENCH_EE and not CONFIG["skip_unchanged_gradient_refresh"]:
+        solver.set_skip_unchanged(1)
+        step_device(); ms3 = 0.0; n3 = max(2, args.steps // 2)
+        for _ in range(n3):
+            ms3 += step_device()[0]
+        optin = {"value": int(d_it.sum().item()) * n3 / (ms3 / 1000.0), "unit": UNIT, "steps": n3,
+                 "note": "pddp_set_skip_unchanged(1): no gradient refresh after a rejected line search; not the default, not the headline"}
+        solver.set_skip_unchanged(0)
     # strong scaling (BASELINE configs[3]): a FIXED global batch of 512 problems split over the ranks, same timing rules; on one GPU
     # this is the 512-problem single-GPU figure the N-GPU values are divided by
     strong = None
@@ -378,6 +390,8 @@ def main():
             s4.freeMemory_GPU()
         if strong is not None:
             out["strong"] = strong
+        if optin is not None:
+            out["optin_skip_unchanged"] = optin
         if ashard is not None:
             out["alpha_sharded"] = ashard
         if world == 1:
