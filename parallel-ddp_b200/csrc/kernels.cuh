@@ -833,7 +833,11 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
             gg[r] = val;
         }
         float *gH = S.H + ((size_t)b*N + k)*H_STRIDE;
-        for (int e = l; e < nm*nm; e += LANES){
+        // The reference rewrites all (n+m)^2 entries at every knot of every iteration; only the 7 x 7 pose block and the diagonal ever change
+        // (the other entries are written as +0 by the initialisation, write_H = 1), so an iteration rewrites those 63 entries
+        const int cnt = write_H ? nm*nm : np*np + (nm - np);
+        for (int i = l; i < cnt; i += LANES){
+            const int e = write_H ? i : (i < np*np ? (i / np)*nm + (i % np) : (i - np*np + np)*(nm + 1));
             const int cc = e / nm, r = e % nm; float val = 0.f;
             if (r < np && cc < np){
                 #pragma unroll
