@@ -960,10 +960,24 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q){
     __syncthreads();
     mpc_copy(xp, cx, N*n); mpc_copy(up, cu, N*m); mpc_copy(dp, cd, N*n);
 }
-// storeVarsGPU_MPC (:755-776) on the device side: success[b] != 0 -> the final trajectory becomes the current plan, else the
-// shifted previous plan and gains come back
-__global__ void mpc_store_kernel(DevState S, MpcState Q, const int *success, float *x_out, float *u_out, float *KT_out){
-    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m;
+// storeVarsGPU_MPC (:755-776) on the device side.  A solve counts as successful when one of its iterations accepted a step size
+// above zero, or when the failure counter was still at zero before the step (`publish_anyway`: it reaches one either way) -- the
+// scan of MPCHelpers.cuh:987-991, done here so that the step needs no host round trip in the middle: the final
+// trajectory then becomes the current plan, else the shifted previous plan and gains come back.  Everything the host wants back
+// is packed behind `pack` -- x | u | KT | alphaOut | Jout | iterations | success -- for a single device-to-host copy.
+__global__ void mpc_store_kernel(DevState S, MpcState Q, const int *publish_anyway, float *pack){
+    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m, B = S.B, L = S.max_iter + 1;
+    float *x_out = pack, *u_out = x_out + (size_t)B*N*n, *KT_out = u_out + (size_t)B*N*m;
+    int *a_out = reinterpret_cast<int*>(KT_out + (size_t)B*N*n*m); float *J_out = reinterpret_cast<float*>(a_out + (size_t)B*L);
+    int *it_out = reinterpret_cast<int*>(J_out + (size_t)B*L), *success = it_out + B;
+    __shared__ int succ_s;
+    const int its = S.iter[b];
+    if (threadIdx.x == 0){
+        int s = publish_anyway[b]; for (int i = 1; i <= its; i++){ if (S.alphaOut[(size_t)b*L + i] > 0){ s = 1; } }
+        succ_s = s; success[b] = s; it_out[b] = its;
+    }
+    for (int i = threadIdx.x; i < L; i += blockDim.x){ a_out[(size_t)b*L + i] = S.alphaOut[(size_t)b*L + i]; J_out[(size_t)b*L + i] = S.Jout[(size_t)b*L + i]; }
+    __syncthreads();
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     const int src = S.final_src[b];
     const float *sx = (src >= 0) ? S.x + ((size_t)b*S.A + src)*N*n : S.xp + (size_t)b*N*n;
@@ -972,7 +986,7 @@ __global__ void mpc_store_kernel(DevState S, MpcState Q, const int *success, flo
     // entries rewritten by the simulation; the other entries are never read by a solve but they shift onto boundaries later
     const float *sdc = S.d + ((size_t)b*S.A + (src >= 0 ? src : 0))*N*n, *sdp = S.dp + (size_t)b*N*n; const int NBF = N / S.M;
     auto sd_at = [&](int i){ const int k = i / n; const bool onb = (((k+1) % NBF) == 0) && (k < N-1); return (src >= 0 && onb) ? sdc[i] : sdp[i]; };
-    if (success[b]){
+    if (succ_s){
         for (int i = threadIdx.x; i < N*n; i += blockDim.x){ const float v = sx[i]; cx[i] = v; x_out[(size_t)b*N*n + i] = v; cd[i] = sd_at(i); }
         for (int i = threadIdx.x; i < N*m; i += blockDim.x){ const float v = su[i]; cu[i] = v; u_out[(size_t)b*N*m + i] = v; }
         for (int i = threadIdx.x; i < N*n*m; i += blockDim.x){ KT_out[(size_t)b*N*n*m + i] = KT[i]; }

@@ -35,6 +35,7 @@ struct pddp_solver {
     bool skip_env = false;
     int next_clear = 1, next_rollout = 0;                                      // loadVarsGPU flags of the next solve
     MpcState mpc{}; int *d_mpc_flags = nullptr; float *d_xActual = nullptr; bool mpc_ready = false;   // receding-horizon state (pddp_mpc_*)
+    float *d_mpc_pack = nullptr, *h_mpc_pack = nullptr; size_t mpc_pack_bytes = 0;     // what a step hands back, packed for one copy (mpc_store_kernel)
     std::vector<int> mpc_lss;                                                  // last_successful_solve per problem (MPCHelpers.cuh:63)
     size_t smem_mpc = 0;
     long launches = 0;
@@ -282,7 +283,7 @@ extern "C" void pddp_destroy(pddp_handle h){
     if (h->nccl.comm && h->nccl.CommDestroy){ h->nccl.CommDestroy(h->nccl.comm); }
     for (auto &e : h->xev){ if (e){ cudaEventDestroy(e); } }
     for (void *p : h->allocs){ cudaFree(p); }
-    if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); }
+    if (h->h_stage){ cudaFreeHost(h->h_stage); } if (h->h_nactive){ cudaFreeHost(h->h_nactive); } if (h->h_mpc_pack){ cudaFreeHost(h->h_mpc_pack); }
     for (auto &e : h->ev){ if (e){ cudaEventDestroy(e); } }
     for (auto &e : h->gev){ cudaEventDestroy(e); }
     for (auto st : h->gstreams){ cudaStreamDestroy(st); }
@@ -654,6 +655,9 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
         h->d_xActual = xa; h->mpc.xActual = xa;
         void *q = nullptr; CK(cudaMalloc(&q, 3*B*sizeof(int))); h->d_mpc_flags = (int*)q; h->allocs.push_back(q);
         h->mpc.shift = h->d_mpc_flags; h->mpc.clear = h->d_mpc_flags + B;
+        h->mpc_pack_bytes = (B*N*(n + m + n*m) + 2*B*((size_t)S.max_iter + 1) + 2*B)*4;
+        q = nullptr; CK(cudaMalloc(&q, h->mpc_pack_bytes)); h->d_mpc_pack = (float*)q; h->allocs.push_back(q);
+        CK(cudaMallocHost((void**)&h->h_mpc_pack, h->mpc_pack_bytes));
         if (!h->ops){
             h->smem_mpc = 2*36*kuka::NB*sizeof(float) + sizeof(SimGroupSmem);
             CK(cudaFuncSetAttribute(mpc_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_mpc));
@@ -691,8 +695,9 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
         if (shiftAmount[b] < 0){ h->err = "negative shiftAmount"; return PDDP_E_INVALID; }
         flags[b] = shiftAmount[b];
         flags[B + b] = (h->mpc_lss[b] > 10 /* SOLVES_TO_RESET, MPCHelpers.cuh:34-36 */ || clear_vars) ? 1 : 0;
+        flags[2*(size_t)B + b] = (h->mpc_lss[b] == 0) ? 1 : 0;     // a counter still at zero reaches one whatever the solve does: publish (:987-991)
     }
-    CK(cudaMemcpyAsync(h->d_mpc_flags, flags.data(), 2*(size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_mpc_flags, flags.data(), 3*(size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
     if (h->use_cost_shift && S.ee){ CK(cudaMemcpyAsync(h->d_cost_shift, flags.data(), (size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream)); S.cost_shift = h->d_cost_shift; }
     CK(cudaMemcpyAsync(h->d_xActual, xActual, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(S.xGoal, xGoal, (size_t)B*n*4, cudaMemcpyHostToDevice, h->stream));
@@ -708,42 +713,26 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     if (!rc){ S.iter_cap = max_iter; rc = run_iterations(h, nullptr, 1); }
     S.iter_cap = S.max_iter; S.cost_shift = nullptr;
     if (rc){ return rc; }
-    // success bookkeeping (MPCHelpers.cuh:987-991, 757-758) needs the step-size trace on the host
-    std::vector<int> aout((size_t)B*L), its(B); std::vector<float> jout((size_t)B*L);
-    CK(cudaMemcpyAsync(aout.data(), S.alphaOut, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(jout.data(), S.Jout, (size_t)B*L*4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(its.data(), S.iter, (size_t)B*4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int b = 0; b < B; b++){
-        for (int i = 1; i <= its[b]; i++){ if (aout[(size_t)b*L + i] > 0){ h->mpc_lss[b] = 0; } }
-        h->mpc_lss[b] += 1;
-        flags[2*(size_t)B + b] = (h->mpc_lss[b] == 1) ? 1 : 0;
-    }
-    CK(cudaMemcpyAsync(h->d_mpc_flags + 2*(size_t)B, flags.data() + 2*(size_t)B, (size_t)B*sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    // results of the successful problems land in pinned staging first, the others keep the caller's previous plan
-    float *sx = h->h_stage, *su = sx + (size_t)B*N*n;
-    float *dKT = h->mpc.tmp;     // the shift scratch doubles as the device-side staging of the published gains
-    mpc_store_kernel<<<B, 256, 0, h->stream>>>(S, h->mpc, h->d_mpc_flags + 2*(size_t)B, h->d_xout, h->d_uout, dKT);
+    // the success scan (MPCHelpers.cuh:987-991, 757-758) runs inside mpc_store_kernel (the counter's value before the step went up with the flags), and everything the caller gets back returns
+    // in one copy to pinned memory: one synchronisation per step.  Successful problems publish their plan and gains, the others keep
+    // the caller's previous plan.
+    mpc_store_kernel<<<B, 256, 0, h->stream>>>(S, h->mpc, h->d_mpc_flags + 2*(size_t)B, h->d_mpc_pack);
     h->launches += 1; CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(sx, h->d_xout, (size_t)B*N*n*4, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(su, h->d_uout, (size_t)B*N*m*4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_mpc_pack, h->d_mpc_pack, h->mpc_pack_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    // gains of the successful problems: runs of consecutive successes travel in one copy each (all of them in one when every solve took a step)
-    for (int b = 0; b < B; ){
-        if (!flags[2*(size_t)B + b]){ b++; continue; }
-        int e = b; while (e < B && flags[2*(size_t)B + e]){ e++; }
-        CK(cudaMemcpyAsync(KT + (size_t)b*N*n*m, dKT + (size_t)b*N*n*m, (size_t)(e - b)*N*n*m*4, cudaMemcpyDeviceToHost, h->stream));
-        b = e;
-    }
-    CK(cudaStreamSynchronize(h->stream));
+    const float *sx = h->h_mpc_pack, *su = sx + (size_t)B*N*n, *sKT = su + (size_t)B*N*m;
+    const int *aout = reinterpret_cast<const int*>(sKT + (size_t)B*N*n*m); const float *jout = reinterpret_cast<const float*>(aout + (size_t)B*L);
+    const int *its = reinterpret_cast<const int*>(jout + (size_t)B*L), *succ = its + B;
     for (int b = 0; b < B; b++){
-        if (flags[2*(size_t)B + b]){
+        h->mpc_lss[b] = succ[b] ? 1 : h->mpc_lss[b] + 1;
+        if (succ[b]){
             std::memcpy(x + (size_t)b*N*n, sx + (size_t)b*N*n, (size_t)N*n*4); std::memcpy(u + (size_t)b*N*m, su + (size_t)b*N*m, (size_t)N*m*4);
+            std::memcpy(KT + (size_t)b*N*n*m, sKT + (size_t)b*N*n*m, (size_t)N*n*m*4);
         }
         if (last_successful_solve){ last_successful_solve[b] = h->mpc_lss[b]; }
         if (iters_out){ iters_out[b] = its[b]; }
     }
-    if (Jout){ std::memcpy(Jout, jout.data(), (size_t)B*L*4); } if (alphaOut){ std::memcpy(alphaOut, aout.data(), (size_t)B*L*4); }
+    if (Jout){ std::memcpy(Jout, jout, (size_t)B*L*4); } if (alphaOut){ std::memcpy(alphaOut, aout, (size_t)B*L*4); }
     return 0;
 }
 
