@@ -195,6 +195,33 @@ __device__ __forceinline__ void mpc_shift(float *A, float *tmp, int shift, int s
     for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x){ const float v = tmp[idx]; A[idx] = v; if (B){ B[idx] = v; } }
     __syncthreads();
 }
+// The same shift without scratch, by `nthr` threads of the CTA (this thread is number `tid` of them; they meet at named barrier `bar`):
+// a slab of 8*nthr entries is read into registers, the barrier passes, the slab is written.  Sources lie at or ahead of their
+// destinations and slabs go front to back, so a slab's reads can only meet the writes of the same slab -- which the barrier orders;
+// the clamped source (the last knot) is never written.  Eight loads in flight per thread instead of one.
+__device__ __forceinline__ void mpc_bar(int bar, int nthr){ asm volatile("bar.sync %0, %1;" :: "r"(bar), "r"(nthr) : "memory"); }
+__device__ __forceinline__ void mpc_shift_part(float *A, int shift, int sz, int dimN, bool flag, float *B, int tid, int nthr, int bar){
+    constexpr int R = 8;
+    const int cnt = (dimN - 1)*sz;
+    for (int base = 0; base < cnt; base += R*nthr){
+        float v[R];
+        #pragma unroll
+        for (int r = 0; r < R; r++){
+            const int idx = base + r*nthr + tid; v[r] = 0.f;
+            if (idx < cnt){
+                const int k = idx / sz, i = idx - k*sz; int ksrc = shift + k; if (ksrc > dimN - 1){ ksrc = dimN - 1; }
+                if (!(flag && ksrc >= dimN - 1)){ v[r] = A[(size_t)ksrc*sz + i]; }
+            }
+        }
+        mpc_bar(bar, nthr);
+        #pragma unroll
+        for (int r = 0; r < R; r++){ const int idx = base + r*nthr + tid; if (idx < cnt){ A[idx] = v[r]; if (B){ B[idx] = v[r]; } } }
+    }
+}
+// slices of the plain loops for a subset of the CTA's threads
+__device__ __forceinline__ void mpc_swap_part(float *A, float *B, int cnt, int tid, int nthr){ for (int i = tid; i < cnt; i += nthr){ const float v = A[i]; A[i] = B[i]; B[i] = v; } }
+__device__ __forceinline__ void mpc_zero_part(float *A, int cnt, int tid, int nthr){ for (int i = tid; i < cnt; i += nthr){ A[i] = 0.f; } }
+__device__ __forceinline__ void mpc_copy_part(float *D, const float *A, int cnt, int tid, int nthr){ for (int i = tid; i < cnt; i += nthr){ D[i] = A[i]; } }
 __device__ __forceinline__ void mpc_swap(float *A, float *B, int cnt){ for (int i = threadIdx.x; i < cnt; i += blockDim.x){ const float v = A[i]; A[i] = B[i]; B[i] = v; } }
 __device__ __forceinline__ void mpc_zero(float *A, int cnt){ for (int i = threadIdx.x; i < cnt; i += blockDim.x){ A[i] = 0.f; } }
 __device__ __forceinline__ void mpc_copy(float *D, const float *A, int cnt){ for (int i = threadIdx.x; i < cnt; i += blockDim.x){ D[i] = A[i]; } }

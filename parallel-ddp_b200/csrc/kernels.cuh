@@ -914,31 +914,24 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q){
     constexpr int n = kuka::NX, m = kuka::NU, LANES = 32;          // the rollout is one trajectory: the whole warp works on it
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b]; const bool clear = Q.clear[b] != 0;
     if (threadIdx.x == 0){ S.init_knot[b] = S.ee ? S.alphaIndex[b] : 0; }      // the slot index the reference's plan lives in (the reset that follows zeroes alphaIndex)
-    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
+    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n;
     float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     float *P0 = S.Pbuf[0] + (size_t)b*N*n*n, *P1 = S.Pbuf[1] + (size_t)b*N*n*n, *p0 = S.pbuf[0] + (size_t)b*N*n, *p1 = S.pbuf[1] + (size_t)b*N*n;
-    // The solve that follows restarts the iteration counter at 1: its first backward pass overwrites Pbuf[1] and seeds its blocks
-    // from Pbuf[0].  The reference seeds them from the (shifted) Pp, the OLDER buffer, so the newer one -- Pbuf[iter & 1] of the
-    // previous solve, whose parity differs between problems that stopped at different iterations -- has to sit in slot 1.
-    if (!clear && (S.iter[b] & 1) == 0){ mpc_swap(P0, P1, N*n*n); mpc_swap(p0, p1, N*n); __syncthreads(); }
+    // The plan itself (x, d, u: small) is shifted by the whole CTA; after that warp 0 integrates the open-loop rollout -- 127 dependent
+    // dynamics evaluations, the long pole of the step -- while warps 1-7 move the big arrays (gains, both cost-to-go buffers) under it.
+    const int t = threadIdx.x, T = blockDim.x;
     if (shift > 0){
-        mpc_shift(cx, tmp, shift, n, N, false, xp);
-        mpc_shift(cd, tmp, shift, n, N, false, nullptr);
-        if (!clear){
-            mpc_shift(cu, tmp, shift, m, N-1, true, up);
-            mpc_shift(KT, tmp, shift, n*m, N-1, true, nullptr);
-            mpc_shift(P0, tmp, shift, n*n, N, false, nullptr); mpc_shift(P1, tmp, shift, n*n, N, false, nullptr);
-            mpc_shift(p0, tmp, shift, n, N, false, nullptr); mpc_shift(p1, tmp, shift, n, N, false, nullptr);
-        }
+        mpc_shift_part(cx, shift, n, N, false, xp, t, T, 0);
+        mpc_shift_part(cd, shift, n, N, false, nullptr, t, T, 0);
+        if (!clear){ mpc_shift_part(cu, shift, m, N-1, true, up, t, T, 0); }
     }
-    if (clear){ mpc_zero(cu, N*m); mpc_zero(KT, N*n*m); mpc_zero(P0, N*n*n); mpc_zero(P1, N*n*n); mpc_zero(p0, N*n); mpc_zero(p1, N*n); }
-    mpc_zero(S.du + (size_t)b*N*m, N*m); mpc_zero(S.dT + (size_t)b*S.A, S.A);
+    if (clear){ mpc_zero(cu, N*m); }
     __syncthreads();
-    // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon, by warp 0
-    if (threadIdx.x < 32){
+    if (t < 32){
+        // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon
         float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
         SimGroupSmem &s = *reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
-        const int l = threadIdx.x;
+        const int l = t;
         for (int i = l; i < 36*kuka::NB; i += 32){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
         __syncwarp();
         kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
@@ -954,19 +947,34 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q){
             if (l < n){ const float v = s.xn[l]; s.x[l] = v; cx[(k+1)*n + l] = v; }
             __syncwarp();
         }
+    } else {
+        const int w = t - 32, W = T - 32;
+        // The solve that follows restarts the iteration counter at 1: its first backward pass overwrites Pbuf[1] and seeds its blocks
+        // from Pbuf[0].  The reference seeds them from the (shifted) Pp, the OLDER buffer, so the newer one -- Pbuf[iter & 1] of the
+        // previous solve, whose parity differs between problems that stopped at different iterations -- has to sit in slot 1.
+        if (!clear && (S.iter[b] & 1) == 0){ mpc_swap_part(P0, P1, N*n*n, w, W); mpc_swap_part(p0, p1, N*n, w, W); mpc_bar(1, W); }
+        if (shift > 0 && !clear){
+            mpc_shift_part(KT, shift, n*m, N-1, true, nullptr, w, W, 1);
+            mpc_shift_part(P0, shift, n*n, N, false, nullptr, w, W, 1); mpc_shift_part(P1, shift, n*n, N, false, nullptr, w, W, 1);
+            mpc_shift_part(p0, shift, n, N, false, nullptr, w, W, 1); mpc_shift_part(p1, shift, n, N, false, nullptr, w, W, 1);
+        }
+        if (clear){ mpc_zero_part(KT, N*n*m, w, W); mpc_zero_part(P0, N*n*n, w, W); mpc_zero_part(P1, N*n*n, w, W); mpc_zero_part(p0, N*n, w, W); mpc_zero_part(p1, N*n, w, W); }
+        mpc_zero_part(S.du + (size_t)b*N*m, N*m, w, W); mpc_zero_part(S.dT + (size_t)b*S.A, S.A, w, W);
+        mpc_bar(1, W);
+        mpc_copy_part(Q.x_old + (size_t)b*N*n, xp, N*n, w, W); mpc_copy_part(Q.u_old + (size_t)b*N*m, up, N*m, w, W);
+        mpc_copy_part(Q.KT_old + (size_t)b*N*n*m, KT, N*n*m, w, W); mpc_copy_part(dp, cd, N*n, w, W);
     }
     __syncthreads();
-    mpc_copy(Q.x_old + (size_t)b*N*n, xp, N*n); mpc_copy(Q.u_old + (size_t)b*N*m, up, N*m); mpc_copy(Q.KT_old + (size_t)b*N*n*m, KT, N*n*m);
-    __syncthreads();
-    mpc_copy(xp, cx, N*n); mpc_copy(up, cu, N*m); mpc_copy(dp, cd, N*n);
+    mpc_copy(xp, cx, N*n); mpc_copy(up, cu, N*m);
 }
 // storeVarsGPU_MPC (:755-776) on the device side.  A solve counts as successful when one of its iterations accepted a step size
 // above zero, or when the failure counter was still at zero before the step (`publish_anyway`: it reaches one either way) -- the
 // scan of MPCHelpers.cuh:987-991, done here so that the step needs no host round trip in the middle: the final
 // trajectory then becomes the current plan, else the shifted previous plan and gains come back.  Everything the host wants back
 // is packed behind `pack` -- x | u | KT | alphaOut | Jout | iterations | success -- for a single device-to-host copy.
+constexpr int MPC_STORE_SPLIT = 8;      // CTAs per problem: the hand-back of a single arm is a copy of 60 KB, too slow for one CTA's loads in flight
 __global__ void mpc_store_kernel(DevState S, MpcState Q, const int *publish_anyway, float *pack){
-    const int b = blockIdx.x, N = S.N, n = S.n, m = S.m, B = S.B, L = S.max_iter + 1;
+    const int b = blockIdx.x / MPC_STORE_SPLIT, t0 = (blockIdx.x % MPC_STORE_SPLIT)*blockDim.x + threadIdx.x, TT = MPC_STORE_SPLIT*blockDim.x, N = S.N, n = S.n, m = S.m, B = S.B, L = S.max_iter + 1;
     float *x_out = pack, *u_out = x_out + (size_t)B*N*n, *KT_out = u_out + (size_t)B*N*m;
     int *a_out = reinterpret_cast<int*>(KT_out + (size_t)B*N*n*m); float *J_out = reinterpret_cast<float*>(a_out + (size_t)B*L);
     int *it_out = reinterpret_cast<int*>(J_out + (size_t)B*L), *success = it_out + B;
@@ -974,9 +982,9 @@ __global__ void mpc_store_kernel(DevState S, MpcState Q, const int *publish_anyw
     const int its = S.iter[b];
     if (threadIdx.x == 0){
         int s = publish_anyway[b]; for (int i = 1; i <= its; i++){ if (S.alphaOut[(size_t)b*L + i] > 0){ s = 1; } }
-        succ_s = s; success[b] = s; it_out[b] = its;
+        succ_s = s; if (t0 == 0){ success[b] = s; it_out[b] = its; }
     }
-    for (int i = threadIdx.x; i < L; i += blockDim.x){ a_out[(size_t)b*L + i] = S.alphaOut[(size_t)b*L + i]; J_out[(size_t)b*L + i] = S.Jout[(size_t)b*L + i]; }
+    for (int i = t0; i < L; i += TT){ a_out[(size_t)b*L + i] = S.alphaOut[(size_t)b*L + i]; J_out[(size_t)b*L + i] = S.Jout[(size_t)b*L + i]; }
     __syncthreads();
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     const int src = S.final_src[b];
@@ -987,13 +995,13 @@ __global__ void mpc_store_kernel(DevState S, MpcState Q, const int *publish_anyw
     const float *sdc = S.d + ((size_t)b*S.A + (src >= 0 ? src : 0))*N*n, *sdp = S.dp + (size_t)b*N*n; const int NBF = N / S.M;
     auto sd_at = [&](int i){ const int k = i / n; const bool onb = (((k+1) % NBF) == 0) && (k < N-1); return (src >= 0 && onb) ? sdc[i] : sdp[i]; };
     if (succ_s){
-        for (int i = threadIdx.x; i < N*n; i += blockDim.x){ const float v = sx[i]; cx[i] = v; x_out[(size_t)b*N*n + i] = v; cd[i] = sd_at(i); }
-        for (int i = threadIdx.x; i < N*m; i += blockDim.x){ const float v = su[i]; cu[i] = v; u_out[(size_t)b*N*m + i] = v; }
-        for (int i = threadIdx.x; i < N*n*m; i += blockDim.x){ KT_out[(size_t)b*N*n*m + i] = KT[i]; }
+        for (int i = t0; i < N*n; i += TT){ const float v = sx[i]; cx[i] = v; x_out[(size_t)b*N*n + i] = v; cd[i] = sd_at(i); }
+        for (int i = t0; i < N*m; i += TT){ const float v = su[i]; cu[i] = v; u_out[(size_t)b*N*m + i] = v; }
+        for (int i = t0; i < N*n*m; i += TT){ KT_out[(size_t)b*N*n*m + i] = KT[i]; }
     } else {
-        for (int i = threadIdx.x; i < N*n; i += blockDim.x){ cx[i] = Q.x_old[(size_t)b*N*n + i]; cd[i] = sd_at(i); }
-        for (int i = threadIdx.x; i < N*m; i += blockDim.x){ cu[i] = Q.u_old[(size_t)b*N*m + i]; }
-        for (int i = threadIdx.x; i < N*n*m; i += blockDim.x){ KT[i] = Q.KT_old[(size_t)b*N*n*m + i]; }
+        for (int i = t0; i < N*n; i += TT){ cx[i] = Q.x_old[(size_t)b*N*n + i]; cd[i] = sd_at(i); }
+        for (int i = t0; i < N*m; i += TT){ cu[i] = Q.u_old[(size_t)b*N*m + i]; }
+        for (int i = t0; i < N*n*m; i += TT){ KT[i] = Q.KT_old[(size_t)b*N*n*m + i]; }
     }
 }
 

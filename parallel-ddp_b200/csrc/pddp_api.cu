@@ -716,7 +716,7 @@ extern "C" int pddp_mpc_step(pddp_handle h, const float *xActual, const float *x
     // the success scan (MPCHelpers.cuh:987-991, 757-758) runs inside mpc_store_kernel (the counter's value before the step went up with the flags), and everything the caller gets back returns
     // in one copy to pinned memory: one synchronisation per step.  Successful problems publish their plan and gains, the others keep
     // the caller's previous plan.
-    mpc_store_kernel<<<B, 256, 0, h->stream>>>(S, h->mpc, h->d_mpc_flags + 2*(size_t)B, h->d_mpc_pack);
+    mpc_store_kernel<<<B*MPC_STORE_SPLIT, 256, 0, h->stream>>>(S, h->mpc, h->d_mpc_flags + 2*(size_t)B, h->d_mpc_pack);
     h->launches += 1; CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->h_mpc_pack, h->d_mpc_pack, h->mpc_pack_bytes, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
