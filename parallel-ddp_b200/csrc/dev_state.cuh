@@ -180,23 +180,12 @@ __global__ void sweep_kernel(DevState S, int splits, int b0){
 struct MpcState {
     float *cx, *cu, *cd;           // [B][N][.] the current plan with its defects (h_d_x/u/d[alphaIndex] of the reference)
     float *x_old, *u_old, *KT_old; // the shifted previous plan, restored when a solve takes no step
-    float *tmp;                    // [B][N*n*n] scratch of the out-of-place shifts
     const float *xActual;          // [B][n]
     const int *shift, *clear;      // [B]
 };
-// shiftAndCopy (MPCHelpers.cuh:425-453): A[k] <- A[min(shift + k, dimN-1)] for k < dimN-1 (zero past the end with `flag`), B likewise
-__device__ __forceinline__ void mpc_shift(float *A, float *tmp, int shift, int sz, int dimN, bool flag, float *B){
-    const int cnt = (dimN - 1)*sz;
-    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x){
-        const int k = idx / sz, i = idx - k*sz; int ksrc = shift + k; if (ksrc > dimN - 1){ ksrc = dimN - 1; }
-        tmp[idx] = (flag && ksrc >= dimN - 1) ? 0.f : A[(size_t)ksrc*sz + i];
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < cnt; idx += blockDim.x){ const float v = tmp[idx]; A[idx] = v; if (B){ B[idx] = v; } }
-    __syncthreads();
-}
-// The same shift without scratch, by `nthr` threads of the CTA (this thread is number `tid` of them; they meet at named barrier `bar`):
-// a slab of 8*nthr entries is read into registers, the barrier passes, the slab is written.  Sources lie at or ahead of their
+// shiftAndCopy (MPCHelpers.cuh:425-453): A[k] <- A[min(shift + k, dimN-1)] for k < dimN-1 (zero past the end with `flag`), B likewise.
+// In place, without the reference's scratch copy, by `nthr` threads of the CTA (this thread is number `tid` of them; they meet at named
+// barrier `bar`): a slab of 8*nthr entries is read into registers, the barrier passes, the slab is written.  Sources lie at or ahead of their
 // destinations and slabs go front to back, so a slab's reads can only meet the writes of the same slab -- which the barrier orders;
 // the clamped source (the last knot) is never written.  Eight loads in flight per thread instead of one.
 __device__ __forceinline__ void mpc_bar(int bar, int nthr){ asm volatile("bar.sync %0, %1;" :: "r"(bar), "r"(nthr) : "memory"); }

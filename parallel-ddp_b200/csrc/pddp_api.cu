@@ -651,7 +651,7 @@ extern "C" int pddp_mpc_init(pddp_handle h, const float *x_init, const float *u_
         auto da = [&](float **p, size_t cnt){ void *q = nullptr; if (cudaMalloc(&q, cnt*4) != cudaSuccess){ return false; } *p = (float*)q; h->allocs.push_back(q); return true; };
         float *xa = nullptr;
         if (!da(&h->mpc.cx, B*N*n) || !da(&h->mpc.cu, B*N*m) || !da(&h->mpc.cd, B*N*n) || !da(&h->mpc.x_old, B*N*n) || !da(&h->mpc.u_old, B*N*m) ||
-            !da(&h->mpc.KT_old, B*N*n*m) || !da(&h->mpc.tmp, B*N*n*n) || !da(&xa, B*n)){ h->err = "cudaMalloc failed (receding-horizon state)"; return PDDP_E_CUDA; }
+            !da(&h->mpc.KT_old, B*N*n*m) || !da(&xa, B*n)){ h->err = "cudaMalloc failed (receding-horizon state)"; return PDDP_E_CUDA; }
         h->d_xActual = xa; h->mpc.xActual = xa;
         void *q = nullptr; CK(cudaMalloc(&q, 3*B*sizeof(int))); h->d_mpc_flags = (int*)q; h->allocs.push_back(q);
         h->mpc.shift = h->d_mpc_flags; h->mpc.clear = h->d_mpc_flags + B;

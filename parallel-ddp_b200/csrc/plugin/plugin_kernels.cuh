@@ -328,19 +328,22 @@ __global__ void plug_mpc_load_kernel(DevState S, MpcState Q){
     __shared__ float s_x[PN], s_u[PM], s_qdd[PNP], s_xn[PN];
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b], l = plug_tid(); const bool clear = Q.clear[b] != 0;
     if (l == 0){ S.init_knot[b] = 0; ::pddp_plugin::rt_num_time_steps() = N; }
-    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n, *tmp = Q.tmp + (size_t)b*N*n*n;
+    float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n;
     float *xp = S.xp + (size_t)b*N*n, *up = S.up + (size_t)b*N*m, *dp = S.dp + (size_t)b*N*n, *KT = S.KT + (size_t)b*N*n*m;
     float *P0 = S.Pbuf[0] + (size_t)b*N*n*n, *P1 = S.Pbuf[1] + (size_t)b*N*n*n, *p0 = S.pbuf[0] + (size_t)b*N*n, *p1 = S.pbuf[1] + (size_t)b*N*n;
     if (!clear && (S.iter[b] & 1) == 0){ mpc_swap(P0, P1, N*n*n); mpc_swap(p0, p1, N*n); __syncthreads(); }      // see mpc_load_kernel (kernels.cuh)
     if (shift > 0){
-        mpc_shift(cx, tmp, shift, n, N, false, xp);
-        mpc_shift(cd, tmp, shift, n, N, false, nullptr);
+        // register-slab shifts (dev_state.cuh): eight loads in flight per thread, no scratch pass
+        const int T = plug_nthreads();
+        mpc_shift_part(cx, shift, n, N, false, xp, l, T, 0);
+        mpc_shift_part(cd, shift, n, N, false, nullptr, l, T, 0);
         if (!clear){
-            mpc_shift(cu, tmp, shift, m, N-1, true, up);
-            mpc_shift(KT, tmp, shift, n*m, N-1, true, nullptr);
-            mpc_shift(P0, tmp, shift, n*n, N, false, nullptr); mpc_shift(P1, tmp, shift, n*n, N, false, nullptr);
-            mpc_shift(p0, tmp, shift, n, N, false, nullptr); mpc_shift(p1, tmp, shift, n, N, false, nullptr);
+            mpc_shift_part(cu, shift, m, N-1, true, up, l, T, 0);
+            mpc_shift_part(KT, shift, n*m, N-1, true, nullptr, l, T, 0);
+            mpc_shift_part(P0, shift, n*n, N, false, nullptr, l, T, 0); mpc_shift_part(P1, shift, n*n, N, false, nullptr, l, T, 0);
+            mpc_shift_part(p0, shift, n, N, false, nullptr, l, T, 0); mpc_shift_part(p1, shift, n, N, false, nullptr, l, T, 0);
         }
+        __syncthreads();
     }
     if (clear){ mpc_zero(cu, N*m); mpc_zero(KT, N*n*m); mpc_zero(P0, N*n*n); mpc_zero(P1, N*n*n); mpc_zero(p0, N*n); mpc_zero(p1, N*n); }
     mpc_zero(S.du + (size_t)b*N*m, N*m); mpc_zero(S.dT + (size_t)b*S.A, S.A);
