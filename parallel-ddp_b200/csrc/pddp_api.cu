@@ -1134,3 +1134,8 @@ extern "C" int pddp_phase_next_iteration(pddp_handle h){ if (!h){ return PDDP_E_
 extern "C" int pddp_last_phase_stats(pddp_handle h, double *ms, int *launches){
     if (!h){ return PDDP_E_INVALID; } if (ms){ *ms = h->last_ms; } if (launches){ *launches = h->last_launches; } return 0;
 }
+
+#ifdef PDDP_SIM_TRACE
+// trace build only: the clock64() stamps of the last forward-dynamics evaluation of block 0 (tools/sim_trace.py)
+extern "C" int pddp_debug_simtrace(long long *out16){ return (int)cudaMemcpyFromSymbol(out16, pddp_simtrace, 16*sizeof(long long)); }
+#endif
