@@ -754,12 +754,15 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
 #else
     const float *sI = S.I, *sTb = S.Tbody;
 #endif
-    if (b >= b0 + nb || S.done[b]){ return; }
+    if (b >= b0 + nb){ return; }
+    // the three per-problem scalars in one round trip (read one after the other -- done, then accepted / alphaIndex behind its
+    // branch -- they were two dependent trips to L2 ahead of the candidate's state, which is a third)
+    const int done_b = S.done[b], accepted_b = S.accepted[b], a = S.alphaIndex[b];
+    if (done_b){ return; }
     NisGroupSmem &s = gsm[w*GPW + grp];
     kuka::init_ws<LANES>(s.ws, &s.gs, sTb, S.grav);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
-    const bool acc = (mode == 2) || ((mode == 0) && S.accepted[b]);      // mode 2: initialisation after a forward rollout
-    const int a = S.alphaIndex[b];
+    const bool acc = (mode == 2) || ((mode == 0) && accepted_b);         // mode 2: initialisation after a forward rollout
     const float *cx = S.x + (((size_t)b*S.A + a)*N + k)*n, *cu = S.u + (((size_t)b*S.A + a)*N + k)*m, *cd = S.d + (((size_t)b*S.A + a)*N + k)*n;
     if (l < n){
         const float xold = gxp[l];
