@@ -266,6 +266,10 @@ int pddp_set_skip_unchanged(pddp_handle h, int on);
 /* self-test: compares the library's reciprocal (pddp_math.cuh rcp_rn) with the IEEE division 1.0f/x the reference
  * compiles to (e.g. DDPHelpers/invHelpers.cuh pivot reciprocals) on all 2^32 float bit patterns; *mismatches = count. */
 int pddp_selftest_rcp(unsigned long long *mismatches);
+/* self-test: compares the branch-free restatement of sinf / cosf the Kuka dynamics use (plant_kuka.cuh sincos_as_library; the
+ * reference calls sin() / cos() on floats, dynamics_arm.cuh:429-479) with the CUDA library's sinf and cosf on all 2^32 float bit
+ * patterns, sign of zero and NaN-ness included; *mismatches = count. */
+int pddp_selftest_sincos(unsigned long long *mismatches);
 
 #ifdef __cplusplus
 }

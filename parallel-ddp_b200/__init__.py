@@ -46,7 +46,7 @@ class Config(C.Structure):
 EXPORTS = ["pddp_default_config_kuka", "pddp_create", "pddp_destroy", "pddp_last_error", "pddp_solve", "pddp_solve_device",
            "pddp_make_inputs_kuka", "pddp_unit_dynamics", "pddp_unit_integrator_gradient", "pddp_set_array", "pddp_get_array",
            "pddp_phase_load_init", "pddp_phase_backward_pass", "pddp_phase_forward_sweep", "pddp_phase_forward_sim",
-           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
+           "pddp_phase_line_search", "pddp_phase_next_iteration", "pddp_last_phase_stats", "pddp_last_launch_count", "pddp_set_groups", "pddp_selftest_rcp", "pddp_selftest_sincos", "pddp_set_warm_start", "pddp_set_start_mode", "pddp_mpc_init", "pddp_mpc_step", "pddp_set_skip_unchanged", "pddp_set_x_target", "pddp_mpc_set_cost_shift",
            "pddp_default_config", "pddp_plant_dims", "pddp_register_plant", "pddp_load_plant_library", "pddp_plant_error", "pddp_make_inputs",
            "pddp_unit_integrator", "pddp_unit_cost", "pddp_last_iteration_times", "pddp_final_max_defect", "pddp_set_graphs", "pddp_last_graph_launch_count", "pddp_alpha_shard_unique_id", "pddp_alpha_shard_init", "pddp_alpha_shard_stats", "pddp_set_bp_shape",
            "pddp_hardware_controls", "pddp_traj_f_encoded_size", "pddp_traj_f_encode", "pddp_traj_f_decode", "pddp_traj_f_pack_reference"]
@@ -84,6 +84,7 @@ def load_library():
     L.pddp_last_launch_count.argtypes = [H]; L.pddp_last_launch_count.restype = C.c_long
     L.pddp_set_groups.argtypes = [H, C.c_int]
     L.pddp_selftest_rcp.argtypes = [C.POINTER(C.c_ulonglong)]
+    L.pddp_selftest_sincos.argtypes = [C.POINTER(C.c_ulonglong)]
     L.pddp_set_warm_start.argtypes = [H, FP, FP, FP, FP]
     L.pddp_set_start_mode.argtypes = [H, C.c_int, C.c_int]
     L.pddp_mpc_init.argtypes = [H, FP, FP]
@@ -212,6 +213,15 @@ def selftest_rcp():
     rc = L.pddp_selftest_rcp(C.byref(bad))
     if rc != 0:
         raise PddpError(f"pddp_selftest_rcp failed ({rc})")
+    return int(bad.value)
+
+
+def selftest_sincos():
+    """Number of float bit patterns on which the dynamics' sin / cos differ from the CUDA library's sinf / cosf (must be 0)."""
+    L = load_library(); bad = C.c_ulonglong(0)
+    rc = L.pddp_selftest_sincos(C.byref(bad))
+    if rc != 0:
+        raise PddpError(f"pddp_selftest_sincos failed ({rc})")
     return int(bad.value)
 
 

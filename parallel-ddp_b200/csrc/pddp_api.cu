@@ -616,6 +616,17 @@ __global__ void selftest_rcp_kernel(unsigned long long *bad){
     }
     if (local){ atomicAdd(bad, local); }
 }
+__global__ void selftest_sincos_kernel(unsigned long long *bad){
+    unsigned long long local = 0;
+    for (unsigned long long v = (unsigned long long)blockIdx.x*blockDim.x + threadIdx.x; v < (1ull << 32); v += (unsigned long long)gridDim.x*blockDim.x){
+        const float x = __uint_as_float((unsigned)v);
+        float s, c; kuka::sincos_as_library(x, s, c);
+        const float rs = sinf(x), rc = cosf(x);
+        const bool same = ((__float_as_uint(s) == __float_as_uint(rs)) || (s != s && rs != rs)) && ((__float_as_uint(c) == __float_as_uint(rc)) || (c != c && rc != rc));
+        local += same ? 0 : 1;
+    }
+    if (local){ atomicAdd(bad, local); }
+}
 }
 // ---------------------------------------------------------------------------------------------------- receding horizon
 // EE_COST: the reference's xTarget argument (costFunc / costGrad cost_arm.cuh:263-281; null for runiLQR_GPU, gv->d_xTarget for
@@ -857,6 +868,15 @@ extern "C" int pddp_selftest_rcp(unsigned long long *mismatches){
     unsigned long long *d = nullptr;
     if (cudaMalloc(&d, 8) != cudaSuccess || cudaMemset(d, 0, 8) != cudaSuccess){ return PDDP_E_CUDA; }
     pddp::selftest_rcp_kernel<<<148*8, 256>>>(d);
+    const cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? 0 : PDDP_E_CUDA;
+}
+extern "C" int pddp_selftest_sincos(unsigned long long *mismatches){
+    if (!mismatches){ return PDDP_E_INVALID; }
+    unsigned long long *d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess || cudaMemset(d, 0, 8) != cudaSuccess){ return PDDP_E_CUDA; }
+    pddp::selftest_sincos_kernel<<<148*8, 256>>>(d);
     const cudaError_t e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? 0 : PDDP_E_CUDA;
