@@ -755,25 +755,36 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     const float *sI = S.I, *sTb = S.Tbody;
 #endif
     if (b >= b0 + nb){ return; }
-    // the three per-problem scalars in one round trip (read one after the other -- done, then accepted / alphaIndex behind its
-    // branch -- they were two dependent trips to L2 ahead of the candidate's state, which is a third)
-    const int done_b = S.done[b], accepted_b = S.accepted[b], a = S.alphaIndex[b];
-    if (done_b){ return; }
+    // Everything this knot reads from global memory is requested before the first wait: the per-problem scalars (read one after the
+    // other behind their branches they were two dependent trips to L2), the constant joint transforms, the current trajectory; the
+    // accepted candidate's state follows as soon as its index is here and travels while the workspace is initialised.  (These waits
+    // were 8 % of the kernel's stall samples.)
     NisGroupSmem &s = gsm[w*GPW + grp];
-    kuka::init_ws<LANES>(s.ws, &s.gs, sTb, S.grav);
     float *gxp = S.xp + ((size_t)b*N + k)*n, *gup = S.up + ((size_t)b*N + k)*m, *gdp = S.dp + ((size_t)b*N + k)*n, *gxp2 = S.xp2 + ((size_t)b*N + k)*n;
+    const int done_b = S.done[b], accepted_b = S.accepted[b], a = S.alphaIndex[b];
+    constexpr int TBQ = (16*kuka::NB + LANES - 1)/LANES;
+    float tbr[TBQ];
+    #pragma unroll
+    for (int q = 0; q < TBQ; q++){ const int e = l + q*LANES, ec = e < 16*kuka::NB ? e : 16*kuka::NB - 1; tbr[q] = sTb[36*(ec >> 4) + (ec & 15)]; }
+    const float xold = gxp[l < n ? l : n-1], uold = gup[l < m ? l : m-1];
+    if (done_b){ return; }
     const bool acc = (mode == 2) || ((mode == 0) && accepted_b);         // mode 2: initialisation after a forward rollout
     const float *cx = S.x + (((size_t)b*S.A + a)*N + k)*n, *cu = S.u + (((size_t)b*S.A + a)*N + k)*m, *cd = S.d + (((size_t)b*S.A + a)*N + k)*n;
+    const bool on_boundary = ((k+1) % (N / S.M)) == 0 && k < N-1;
+    const float xcand = cx[l < n ? l : n-1], ucand = cu[l < m ? l : m-1], dcand = cd[l < n ? l : n-1];
+    // kuka::init_ws with the joint transforms from the registers above
+    if (l == 0){ s.ws.grav = S.grav; }
+    #pragma unroll
+    for (int q = 0; q < TBQ; q++){ const int e = l + q*LANES; if (e < 16*kuka::NB){ s.ws.Tb[e] = tbr[q]; s.gs.dTb[e] = 0.f; } }
     if (l < n){
-        const float xold = gxp[l];
-        const float xv = acc ? cx[l] : xold; s.x[l] = xv;
+        const float xv = acc ? xcand : xold; s.x[l] = xv;
         gxp2[l] = (mode == 2) ? xv : xold;                         // xp2 <- xp (fpHelpers.cuh:371); initAlgGPU sets both to the start trajectory (nisInitHelpers.cuh:378-379)
         // defects: a candidate's array is the broadcast copy of dp (memcpyCurrAKern, nisInitHelpers.cuh:22-32) with the interval-
         // boundary entries rewritten by the simulation, so only those change hands; the others are never read by a solve but the
         // receding-horizon shift moves them onto boundaries later
-        if (acc){ gxp[l] = xv; if (((k+1) % (N / S.M)) == 0 && k < N-1){ gdp[l] = cd[l]; } }
+        if (acc){ gxp[l] = xv; if (on_boundary){ gdp[l] = dcand; } }
     }
-    if (l < m){ const float uv = acc ? cu[l] : gup[l]; s.u[l] = uv; if (acc){ gup[l] = uv; } }
+    if (l < m){ const float uv = acc ? ucand : uold; s.u[l] = uv; if (acc){ gup[l] = uv; } }
     // opt-in (pddp_set_skip_unchanged): after a rejected line search the trajectory, hence AB, H and g, are unchanged; the
     // reference recomputes them all the same (nisInitHelpers.cuh:245-279) and so does the default here
     if (S.skip_unchanged && mode == 0 && !acc){ return; }
