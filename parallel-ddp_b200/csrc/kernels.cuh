@@ -922,10 +922,34 @@ __global__ void store_kernel(DevState S, float *x_out, float *u_out, int *iters_
     if (threadIdx.x == 0 && iters_out){ iters_out[b] = S.iter[b]; }
 }
 
+// rolloutMPC<NUM_TIME_STEPS> (MPCHelpers.cuh:524-556): open loop from the measured state over the whole horizon, by one warp.  Out of
+// line on purpose: inlined, the compiler laid the copy code of the other warps into the middle of this loop, whose body then
+// spanned 44 KB -- more than the 32 KB instruction cache behind a lone warp -- instead of the 28 KB it has in the simulation kernel.
+__device__ __noinline__ void mpc_rollout(const float *I, const float *Tbody, float grav, float dt, unsigned char *smem_raw, const float *xActual, float *cx, const float *cu, int N){
+    constexpr int n = kuka::NX, m = kuka::NU, LANES = 32;
+    float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
+    SimGroupSmem &s = *reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
+    const int l = threadIdx.x;
+    for (int i = l; i < 36*kuka::NB; i += 32){ sI[i] = I[i]; sTb[i] = Tbody[i]; }
+    __syncwarp();
+    kuka::init_ws<LANES>(s.ws, nullptr, sTb, grav);
+    const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
+    float Ib[36]; kuka::load_body_inertia<LANES>(I, Ib);
+    if (l < n){ const float v = xActual[l]; s.x[l] = v; cx[l] = v; }
+    for (int k = 0; k < N-1; k++){
+        if (l < m){ s.u[l] = cu[k*m + l]; }
+        __syncwarp();
+        kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix);
+        if (l < kuka::NB){ s.xn[l] = FMA(dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(dt, s.qdd[l], s.x[l+kuka::NB]); }
+        __syncwarp();
+        if (l < n){ const float v = s.xn[l]; s.x[l] = v; cx[(k+1)*n + l] = v; }
+        __syncwarp();
+    }
+}
 // loadVarsGPU_MPC (MPCHelpers.cuh:602-657) followed by the hand-over initAlgGPU does (xp, up, dp <- current plan)
 __global__ void mpc_load_kernel(DevState S, MpcState Q){
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int n = kuka::NX, m = kuka::NU, LANES = 32;          // the rollout is one trajectory: the whole warp works on it
+    constexpr int n = kuka::NX, m = kuka::NU;
     const int b = blockIdx.x, N = S.N, shift = Q.shift[b]; const bool clear = Q.clear[b] != 0;
     if (threadIdx.x == 0){ S.init_knot[b] = S.ee ? S.alphaIndex[b] : 0; }      // the slot index the reference's plan lives in (the reset that follows zeroes alphaIndex)
     float *cx = Q.cx + (size_t)b*N*n, *cu = Q.cu + (size_t)b*N*m, *cd = Q.cd + (size_t)b*N*n;
@@ -942,25 +966,7 @@ __global__ void mpc_load_kernel(DevState S, MpcState Q){
     if (clear){ mpc_zero(cu, N*m); }
     __syncthreads();
     if (t < 32){
-        // rolloutMPC<NUM_TIME_STEPS> (:524-556): open loop from the measured state over the whole horizon
-        float *sI = reinterpret_cast<float*>(smem_raw); float *sTb = sI + 36*kuka::NB;
-        SimGroupSmem &s = *reinterpret_cast<SimGroupSmem*>(sTb + 36*kuka::NB);
-        const int l = t;
-        for (int i = l; i < 36*kuka::NB; i += 32){ sI[i] = S.I[i]; sTb[i] = S.Tbody[i]; }
-        __syncwarp();
-        kuka::init_ws<LANES>(s.ws, nullptr, sTb, S.grav);
-        const kuka::FwdIdx<LANES> fix = kuka::make_fwd_idx<LANES>();
-        float Ib[36]; kuka::load_body_inertia<LANES>(S.I, Ib);
-        if (l < n){ const float v = Q.xActual[b*n + l]; s.x[l] = v; cx[l] = v; }
-        for (int k = 0; k < N-1; k++){
-            if (l < m){ s.u[l] = cu[k*m + l]; }
-            __syncwarp();
-            kuka::forward_sim<LANES>(s.ws, Ib, s.x, s.u, s.qdd, fix);
-            if (l < kuka::NB){ s.xn[l] = FMA(S.dt, s.x[l+kuka::NB], s.x[l]); s.xn[l+kuka::NB] = FMA(S.dt, s.qdd[l], s.x[l+kuka::NB]); }
-            __syncwarp();
-            if (l < n){ const float v = s.xn[l]; s.x[l] = v; cx[(k+1)*n + l] = v; }
-            __syncwarp();
-        }
+        mpc_rollout(S.I, S.Tbody, S.grav, S.dt, smem_raw, Q.xActual + b*n, cx, cu, N);
     } else {
         const int w = t - 32, W = T - 32;
         // The solve that follows restarts the iteration counter at 1: its first backward pass overwrites Pbuf[1] and seeds its blocks
