@@ -878,10 +878,12 @@ __global__ void __launch_bounds__(32*NIS_WARPS) nis_kernel(DevState S, int mode,
     if (fin){ return; }
     float *gAB = S.AB + ((size_t)b*N + k)*AB_STRIDE;
     const float dt = S.dt;
-    for (int e = l; e < n*nm; e += LANES){
-        const int ky = e / n, kx = e % n;
-        const float dxd = kx < np ? ((kx + np == ky) ? 1.f : 0.f) : s.dqdd[(ky-1)*np + kx];
-        gAB[e] = FMA(dt, dxd, (ky == kx) ? 1.f : 0.f);
+    // entry (row kx, column ky): 1[ky == kx] + dt * (kx < np ? 1[ky == kx + np] : dqdd[kx - np, ky]); a lane takes the pair of entries
+    // (r, ky), (np + r, ky) of dqdd's element j = ky*np + r: half the trips of a loop over all n*nm entries, no index arithmetic per half
+    for (int j = l; j < np*nm; j += LANES){
+        const int ky = j / np, r = j - ky*np;
+        gAB[ky*n + r] = FMA(dt, (r + np == ky) ? 1.f : 0.f, (ky == r) ? 1.f : 0.f);
+        gAB[ky*n + np + r] = FMA(dt, s.dqdd[j], (ky == np + r) ? 1.f : 0.f);
     }
 }
 
